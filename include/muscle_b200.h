@@ -1,0 +1,177 @@
+/*
+ * muscle_b200.h -- C ABI of libmuscle_b200.so: the PyMuscle per-step hot path
+ * (motor-neuron pool -> muscle fibers -> per-muscle total) as hand-written
+ * sm_100a CUDA kernels.
+ *
+ * The reference (iandanforth/pymuscle v0.1.2) is pure Python/NumPy and has no
+ * FFI of its own; the boundary it offers is the Python class surface
+ *     Muscle.step                      pymuscle/muscle.py:65-92
+ *     StandardMuscle.step              pymuscle/muscle.py:258-279
+ *     PotvinFuglevand2017MotorNeuronPool.step   pymuscle/potvin_fuglevand_2017_motor_neuron_pool.py:283-295
+ *     PotvinFuglevand2017MuscleFibers.step      pymuscle/potvin_fuglevand_2017_muscle_fibers.py:284-300
+ *     PyMuscleFibers._update_fatigue            pymuscle/pymuscle_fibers.py:80-141
+ * Each entry point below names the reference method(s) it replaces.  The Python
+ * package pymuscle_b200 binds these with ctypes (see INTEGRATION.md for the
+ * stub a maintainer of the reference would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross the boundary;
+ *   - every `*_dev` pointer is a DEVICE pointer owned by the caller (a torch
+ *     tensor kept alive by the Python side); nothing is allocated, freed or
+ *     synchronised here; work is enqueued on `stream` (a cudaStream_t passed as
+ *     void*; NULL = legacy default stream);
+ *   - return value 0 = success, negative MB_E* otherwise; mb_last_error() gives
+ *     a thread-local human-readable message for the last failure;
+ *   - the library is stateless: all simulator state lives in the caller's
+ *     `cpf` / `dur` arrays (float64 in both precision modes).
+ *
+ * Batch layout ("rows x segments")
+ *   A batch is `rows` independent rows; each row holds `S` muscles (segments)
+ *   laid out back to back, `L` = sum of their unit counts.  Per-unit arrays are
+ *   [rows, L] row-major, per-muscle arrays [rows, S].  seg_off[S+1] (int32,
+ *   device) gives the unit offset of each segment inside a row; NULL means one
+ *   muscle of L units per row (the uniform case, e.g. 65,536 x 120).  The
+ *   per-unit parameter table has L entries and is shared by all rows.
+ */
+#ifndef MUSCLE_B200_H
+#define MUSCLE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MB_ABI_VERSION 1
+
+enum MbStatus { MB_OK = 0, MB_EINVAL = -1, MB_EUNSUPPORTED = -2, MB_ECUDA = -3 };
+
+/* Arithmetic mode.  MB_F32: float per-step arithmetic, compensated / float64
+ * state (rtol 1e-4 over 10,000 steps); MB_F64: float64 throughout (rtol 1e-9).
+ * Excitations, forces and totals have the mode's element type; cpf/dur are
+ * float64 in both.  The recruitment mask is bit-exact in both modes. */
+enum MbPrecision { MB_F32 = 0, MB_F64 = 1 };
+
+/* Which fibers model updates the capacities: Potvin & Fuglevand 2017
+ * (fibers:96-115) or PyMuscleFibers with recovery + upper clamp (pmf:80-141). */
+enum MbFibers { MB_FIBERS_POTVIN = 0, MB_FIBERS_PYMUSCLE = 1 };
+
+/* Which half of Muscle.step a single-step launch runs. */
+enum MbStage {
+    MB_STAGE_MUSCLE = 0,   /* excitation -> forces, totals  (Muscle.step, muscle.py:65-92)            */
+    MB_STAGE_POOL   = 1,   /* excitation -> adapted firing rates       (Pool.step, pool:283-295)       */
+    MB_STAGE_FIBERS = 2    /* firing rates -> forces, totals           (Fibers.step, fibers:284-300)   */
+};
+
+/* Scalar hyper-parameters: the constructor arguments of the reference models
+ * that are not per-unit tables (pool:53-66, fibers:46-56, muscle.py:152-187). */
+typedef struct MbConfig {
+    int32_t precision;            /* MbPrecision */
+    int32_t fibers_kind;          /* MbFibers */
+    int32_t central_fatigue;      /* Pool(apply_fatigue=...)    pool:65,193 */
+    int32_t peripheral_fatigue;   /* Fibers(apply_fatigue=...)  fibers:55,279 */
+    double max_recruitment_threshold;   /* RR   pool:56  */
+    double firing_gain;                 /* g    pool:57  */
+    double min_firing_rate;             /* minR pool:58  */
+    double derecruitment_delta;         /* d    pool:61  */
+    double adaptation_magnitude;        /* phi  pool:62  */
+    double adaptation_time_constant;    /* tau  pool:63  */
+    double max_duration;                /*      pool:64  */
+    double contraction_time_change_ratio; /*    fibers:54 */
+    double input_scale;    /* 1, or Pool.max_excitation for StandardMuscle (muscle.py:275) */
+    double output_divisor; /* 1, or StandardMuscle.max_arb_output          (muscle.py:278) */
+    int32_t table_props;   /* MbTableProps bits returned by mb_params_pack for the table in use */
+    int32_t reserved;
+} MbConfig;
+
+/* Facts about a packed table that let the fused kernel drop provably dead clamps. */
+enum MbTableProps {
+    MB_PROP_ADAPT_NONNEG = 1   /* the adaptation of a recruited unit is never negative (pool:221 is a no-op) */
+};
+
+int mb_abi_version(void);
+const char* mb_last_error(void);
+
+/* ---- parameter tables (host) ------------------------------------------------------
+ * Packs the reference's per-unit float64 tables (built by the caller with NumPy so
+ * that thresholds are bit-identical to pool:263-281 etc.) into the mode-specific
+ * 128-bit-vector layout the kernels load.  For MB_F32 this also derives, per unit,
+ * the critical float32 input at which the reference's float64 recruitment predicate
+ * (pool:169-172, after muscle.py:275's scaling) flips, so the FP32 mask is exact.
+ * `rec` may be NULL for MB_FIBERS_POTVIN.  `out_host` receives mb_params_bytes()
+ * bytes which the caller uploads to the device; `table_props` receives MbTableProps bits
+ * that the caller copies into MbConfig.table_props for later launches. */
+size_t mb_params_bytes(const MbConfig* cfg, int64_t L);
+int mb_params_pack(const MbConfig* cfg, int64_t L,
+                   const double* thr, const double* peak, const double* ptf,
+                   const double* ct, const double* fat, const double* rec,
+                   void* out_host, int32_t* table_props /* out, may be NULL */);
+
+/* ---- K1: one step for the whole batch, one launch (HBM-bound) -----------------------
+ * Replaces, for every muscle of the batch at once, Muscle.step / StandardMuscle.step
+ * (stage MUSCLE), Pool.step (stage POOL) or Fibers.step (stage FIBERS).
+ *   in_dev        stage MUSCLE/POOL: excitations; stage FIBERS: firing rates.
+ *                 [rows, S] when in_per_unit == 0 (one value per muscle, the scalar form of
+ *                 muscle.py:81-86), [rows, L] when in_per_unit == 1 (the ndarray form).
+ *   cpf_dev       [rows, L] float64 current peak forces   (fibers:63, R/W unless stage POOL)
+ *   dur_dev       [rows, L] float64 recruitment durations (pool:79,   R/W unless stage FIBERS)
+ *   forces_dev    [rows, L] per-unit forces = Muscle.current_forces (fibers:258); may be NULL
+ *   seg_div_dev   [S] float64 per-segment output divisors (each StandardMuscle of a ragged row
+ *                 has its own max_arb_output, muscle.py:187); NULL = cfg->output_divisor for all
+ *   totals_dev    [rows, S] per-muscle totals (fibers:276, / output divisor); may be NULL
+ *   mask_dev      [rows, L] uint8 recruitment mask (pool:171); may be NULL
+ *   rates_dev     [rows, L] adapted firing rates (Pool.step's return); NULL unless wanted
+ */
+int mb_step(const MbConfig* cfg, const void* params_dev,
+            int64_t rows, int64_t L, int32_t S, const int32_t* seg_off_dev,
+            const double* seg_div_dev,
+            int32_t stage, const void* in_dev, int32_t in_per_unit,
+            double* cpf_dev, double* dur_dev,
+            void* forces_dev, void* totals_dev, uint8_t* mask_dev, void* rates_dev,
+            double step_size, void* stream);
+
+/* ---- K2: K fused steps, state in registers (FP32/FP64-pipe-bound) --------------------
+ * Equivalent to K successive Muscle.step calls on each of `M` identical muscles of `n`
+ * units (uniform layout only: rows = M, L = n, S = 1).
+ *   exc_dev          excitations, element (k, m) at exc_dev[k * exc_stride_k + m];
+ *                    exc_stride_k == 0 means one constant value per muscle for the window
+ *   totals_dev       totals, element (k, m) at totals_dev[k * totals_stride_k + m]; may be NULL
+ *   forces_every     f > 0: per-unit forces (and masks) of steps f-1, 2f-1, ... are written to
+ *                    forces_dec_dev[(k / f), m, u] / mask_dec_dev; 0 = never
+ *   forces_last_dev  [M, n] forces of the window's last step (current_forces); may be NULL
+ * Returns MB_EUNSUPPORTED when n is outside the fused kernel's range (2..512); the
+ * caller then issues K mb_step launches instead (still on the GPU).
+ */
+int mb_step_fused(const MbConfig* cfg, const void* params_dev,
+                  int64_t M, int32_t n, int32_t K,
+                  const void* exc_dev, int64_t exc_stride_k,
+                  double* cpf_dev, double* dur_dev,
+                  void* totals_dev, int64_t totals_stride_k,
+                  void* forces_dec_dev, uint8_t* mask_dec_dev, int32_t forces_every,
+                  void* forces_last_dev,
+                  double step_size, int32_t units_per_thread /* 0 = auto */, void* stream);
+
+/* Launch geometry mb_step_fused would use (for reporting): muscles per block,
+ * threads per block, blocks, dynamic shared memory bytes. */
+int mb_fused_geometry(const MbConfig* cfg, int64_t M, int32_t n, int32_t K, int32_t units_per_thread,
+                      int32_t* muscles_per_block, int32_t* threads, int64_t* blocks, int32_t* smem_bytes);
+
+/* ---- per-muscle capacity sums: StandardMuscle.get_peripheral_fatigue (muscle.py:248-256)
+ * fatigue[rows, S] = 1 - sum(cpf) / output_divisor, as float64. */
+int mb_peripheral_fatigue(const MbConfig* cfg, int64_t rows, int64_t L, int32_t S,
+                          const int32_t* seg_off_dev, const double* seg_div_dev, const double* cpf_dev,
+                          double* fatigue_dev, void* stream);
+
+/* ---- roofline denominators that MEASURED_PEAKS.json does not carry -------------------
+ * Dependent-FMA-chain microkernels: each launch executes
+ *     blocks * threads * chains * iters   FFMA (kind 0) / DFMA (kind 1) / MUFU.EX2 (kind 2)
+ * lane-operations.  The caller times the launch with CUDA events.  `sink_dev` needs
+ * blocks*threads elements of 8 bytes. */
+int mb_peak_probe(int32_t kind, int32_t blocks, int32_t threads, int32_t iters,
+                  void* sink_dev, int64_t* lane_ops, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MUSCLE_B200_H */

@@ -1,0 +1,176 @@
+// mb_core.cuh -- per-motor-unit arithmetic shared by the single-step (K1) and
+// fused (K2) kernels.  One call = one unit, one step; SURVEY.md Appendix A.2
+// lists the reference operations line by line.  Citations: pool: =
+// pymuscle/potvin_fuglevand_2017_motor_neuron_pool.py, fibers: =
+// pymuscle/potvin_fuglevand_2017_muscle_fibers.py, pmf: = pymuscle/pymuscle_fibers.py.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mb {
+
+// ----------------------------------------------------------------------------------
+// Packed per-unit parameters.  The table is L units long and stored as groups of
+// 128-bit vectors, [group][unit], so that a warp of consecutive units issues fully
+// coalesced LDG.128s.  mb_params_pack() (host) is the only writer.
+// ----------------------------------------------------------------------------------
+constexpr int kGroupsF32 = 3;   // float4  x 3 per unit
+constexpr int kGroupsF64 = 5;   // double2 x 5 per unit
+
+struct UnitF {
+    float crit;    // smallest float32 input for which the reference's float64 predicate recruits (pool:169-172)
+    float thr_g;   // gain * (thr - minR):            r = x*gain_e - thr_g            (pool:169-173)
+    float peak;    // peak firing rate                                                (pool:176-177)
+    float phir;    // phi * ratio,  ratio = (thr-1)/(RR-1)                            (pool:231-232)
+    float phir6;   // phi * ratio * (minR - d):       q = r*phir - phir6
+    float ctA;     // kappa * ct * (1 + ccr) / 1000        (kappa: see kKappa below)
+    float ctB;     // kappa * ct * ccr / (1000 * ptf):  kappa*ct_cur/1000 = ctA - ctB*cpf  (fibers:123-125, :220)
+    float fat;     // nominal fatigability                                             (fibers:110)
+    float ptf;     // peak twitch force (upper clamp)                                  (pmf:104-105)
+    float rec;     // recovery rate                                                    (pmf:140)
+    float rdi;     // rec / ptf:  recovery = (rec - rdi*cpf) * dt                      (pmf:137-140)
+};
+
+struct UnitD {
+    double thr, peak, phir, phir6, ctA, ctB, fat, ptf, rec, rdi;
+};
+
+__device__ __forceinline__ UnitF load_unit(const float4* __restrict__ P, int64_t L, int64_t i) {
+    const float4 a = __ldg(P + i), b = __ldg(P + L + i), c = __ldg(P + 2 * L + i);
+    UnitF u;
+    u.crit = a.x; u.thr_g = a.y; u.peak = a.z; u.phir = a.w;
+    u.phir6 = b.x; u.ctA = b.y; u.ctB = b.z; u.fat = b.w;
+    u.ptf = c.x; u.rec = c.y; u.rdi = c.z;
+    return u;
+}
+
+__device__ __forceinline__ UnitD load_unit(const double2* __restrict__ P, int64_t L, int64_t i) {
+    const double2 a = __ldg(P + i), b = __ldg(P + L + i), c = __ldg(P + 2 * L + i),
+                  d = __ldg(P + 3 * L + i), e = __ldg(P + 4 * L + i);
+    UnitD u;
+    u.thr = a.x; u.peak = a.y; u.phir = b.x; u.phir6 = b.y; u.ctA = c.x; u.ctB = c.y;
+    u.fat = d.x; u.ptf = d.y; u.rec = e.x; u.rdi = e.y;
+    return u;
+}
+
+// Scalars derived from MbConfig by the launcher (host, float64) -- passed by value.
+struct ScalF {
+    float gain_e;     // firing_gain * input_scale
+    float adk;        // -log2(e) / tau            : exp(-dur/tau) = ex2(dur * adk)
+    float argmin;     // -max_duration*log2(e)/tau : lower bound of the exponent
+    float c25k;       // ((1 - exp(-2*0.4^3)) / 0.4) / kappa      (fibers:240-241)
+    float ythr;       // 0.4 * kappa                               (fibers:233-236)
+    float inv_out;    // 1 / output_divisor
+};
+struct ScalD {
+    double input_scale, min_rate, gain, mitau /* -1/tau */, max_dur, c25, out_div;
+};
+
+// FP32 mode folds the sigmoid's constant into the contraction-time factors: with
+// kappa = cbrt(2*log2(e)) and y = kappa*x,  exp(-2*x^3) = ex2(-(y*y*y)).  UnitF::ctA/ctB
+// are stored pre-multiplied by kappa.
+constexpr double kKappa = 1.4236443587288568;   // cbrt(2 * 1.4426950408889634)
+constexpr double kLinThrD = 0.4;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// ----------------------------------------------------------------------------------
+// FP32 mode
+// ----------------------------------------------------------------------------------
+
+// Recruitment decision and the un-thresholded rate min(gain*(e - thr + minR), peak).
+// The mask is one compare against the host-derived critical input, which reproduces
+// the float64 predicate bit for bit; the rate value itself only
+// needs float accuracy.  The caller zeroes the rate (or what follows from it) when
+// the unit is not recruited.
+__device__ __forceinline__ float pool_rate_raw(const UnitF& p, const ScalF& s, float x, bool& on) {
+    on = (x >= p.crit);
+    return fminf(fmaf(x, s.gain_e, -p.thr_g), p.peak);
+}
+
+// Adaptation a = q * (1 - exp(-dur/tau)),  q = phi*(r - minR + d)*ratio   (pool:208-233).
+// dur_arg = dur * adk (<= 0), dur BEFORE this step's update.  NOT yet clamped at 0.
+__device__ __forceinline__ float pool_adaptation(const UnitF& p, float r, float dur_arg) {
+    const float q = fmaf(r, p.phir, -p.phir6);
+    const float ex = ex2_approx(dur_arg);
+    return fmaf(-q, ex, q);
+}
+
+// Normalised force and unit force for firing rate fr at capacity cpf
+// (fibers:211-259).  Branch-free: both curve pieces are evaluated.
+__device__ __forceinline__ float fibers_force(const UnitF& p, const ScalF& s, float fr, float cpf, float& nf) {
+    const float ctk = fmaf(cpf, -p.ctB, p.ctA);      // kappa * ct_cur / 1000
+    const float y = ctk * fr;
+    const float lin = y * s.c25k;
+    const float y2 = y * y;
+    const float sig = 1.0f - ex2_approx(-(y2 * y));
+    nf = (y <= s.ythr) ? lin : sig;
+    return nf * cpf;
+}
+
+// ----------------------------------------------------------------------------------
+// FP64 mode.  The three operations that define the recruitment mask keep the
+// reference's order and are protected from FMA contraction; everything else may
+// be re-associated (< 5e-14 over 10,000 steps).
+// ----------------------------------------------------------------------------------
+__device__ __forceinline__ double pool_rate(const UnitD& p, const ScalD& s, double x, bool& on) {
+    const double e = __dmul_rn(x, s.input_scale);                       // muscle.py:275
+    const double r0 = __dadd_rn(__dsub_rn(e, p.thr), s.min_rate);       // pool:169-170
+    on = !(r0 < s.min_rate);                                            // pool:171
+    const double r = (on ? r0 : 0.0) * s.gain;                          // pool:172-173
+    return (r > p.peak) ? p.peak : r;                                   // pool:176-177
+}
+
+__device__ __forceinline__ double pool_adapt(const UnitD& p, const ScalD& s, double r, double dur) {
+    const double q = fma(r, p.phir, -p.phir6);
+    const double a = q * (1.0 - exp(dur * s.mitau));
+    return r - ((a < 0.0) ? 0.0 : a);
+}
+
+__device__ __forceinline__ double fibers_force(const UnitD& p, const ScalD& s, double fr, double cpf, double& nf) {
+    const double ctk = fma(cpf, -p.ctB, p.ctA);
+    const double x = ctk * fr;
+    if (x <= kLinThrD) {
+        nf = x * s.c25;
+    } else {
+        nf = 1.0 - exp(-2.0 * (x * x * x));
+    }
+    return nf * cpf;
+}
+
+// Capacity update, float64 state (used by K1 in both modes and by K2 in FP64 mode).
+// fatdt = fat*dt, recdt = rec*dt, rdidt = rdi*dt (all zero when peripheral fatigue is off).
+template <bool RECOVERY>
+__device__ __forceinline__ double fatigue_update(double cpf, double nf, double fatdt, double recdt,
+                                                 double rdidt, double ptf) {
+    double c = fma(-nf, fatdt, cpf);                                    // fibers:110-111
+    if (RECOVERY) {
+        if (nf <= 0.0) c += fma(-c, rdidt, recdt);                      // pmf:121-141
+    }
+    c = (c < 0.0) ? 0.0 : c;                                            // fibers:114
+    if (RECOVERY) c = (c > ptf) ? ptf : c;                              // pmf:104-105
+    return c;
+}
+
+__device__ __forceinline__ double duration_update(double dur, bool firing, double dt, double max_dur) {
+    double d = firing ? dur + dt : dur;                                 // pool:196-197
+    d = (d > max_dur) ? max_dur : d;                                    // pool:202-203
+    return (d < 0.0) ? 0.0 : d;                                         // pool:205-206
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace mb

@@ -1,0 +1,619 @@
+// muscle_b200.cu -- sm_100a kernels + C ABI (include/muscle_b200.h) for the
+// PyMuscle per-step hot path.  See DESIGN.md for the data layout and the
+// roofline of each kernel.
+//
+//   K1  k1_step<T>        one step, one launch, thread per motor unit, HBM-bound
+//   K2  k2_fused_*        K steps per launch, state in registers, FP-pipe-bound
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared ...
+#include "../../include/muscle_b200.h"
+#include "mb_core.cuh"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+
+using namespace mb;
+
+// =====================================================================================
+// error plumbing
+// =====================================================================================
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define MB_CUDA_OK(expr)                                                                   \
+    do {                                                                                   \
+        cudaError_t e__ = (expr);                                                          \
+        if (e__ != cudaSuccess) return fail(MB_ECUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
+    } while (0)
+
+extern "C" int mb_abi_version(void) { return MB_ABI_VERSION; }
+extern "C" const char* mb_last_error(void) { return g_err; }
+
+static int check_cfg(const MbConfig* c) {
+    if (!c) return fail(MB_EINVAL, "cfg is NULL");
+    if (c->precision != MB_F32 && c->precision != MB_F64) return fail(MB_EINVAL, "bad precision %d", c->precision);
+    if (c->fibers_kind != MB_FIBERS_POTVIN && c->fibers_kind != MB_FIBERS_PYMUSCLE)
+        return fail(MB_EINVAL, "bad fibers_kind %d", c->fibers_kind);
+    if (!(c->adaptation_time_constant > 0)) return fail(MB_EINVAL, "adaptation_time_constant must be > 0");
+    if (!(c->firing_gain > 0)) return fail(MB_EINVAL, "firing_gain must be > 0");
+    if (!(c->output_divisor > 0)) return fail(MB_EINVAL, "output_divisor must be > 0");
+    if (!(c->input_scale > 0)) return fail(MB_EINVAL, "input_scale must be > 0");
+    return MB_OK;
+}
+
+static const double kLog2e = 1.4426950408889634074;
+static const double kLinScale = 1.0 - std::exp(-2.0 * (0.4 * 0.4 * 0.4));   // fibers:241
+
+static ScalF scal_f(const MbConfig& c) {
+    ScalF s;
+    s.gain_e = (float)(c.firing_gain * c.input_scale);
+    s.adk = (float)(-kLog2e / c.adaptation_time_constant);
+    s.argmin = (float)(-c.max_duration * kLog2e / c.adaptation_time_constant);
+    s.c25k = (float)(kLinScale / 0.4 / kKappa);
+    s.ythr = (float)(0.4 * kKappa);
+    s.inv_out = (float)(1.0 / c.output_divisor);
+    return s;
+}
+static ScalD scal_d(const MbConfig& c) {
+    ScalD s;
+    s.input_scale = c.input_scale;
+    s.min_rate = c.min_firing_rate;
+    s.gain = c.firing_gain;
+    s.mitau = -1.0 / c.adaptation_time_constant;
+    s.max_dur = c.max_duration;
+    s.c25 = kLinScale / 0.4;
+    s.out_div = c.output_divisor;
+    return s;
+}
+
+// =====================================================================================
+// parameter packing (host)
+// =====================================================================================
+extern "C" size_t mb_params_bytes(const MbConfig* cfg, int64_t L) {
+    if (!cfg || L <= 0) return 0;
+    return cfg->precision == MB_F32 ? (size_t)L * kGroupsF32 * sizeof(float4)
+                                    : (size_t)L * kGroupsF64 * sizeof(double2);
+}
+
+// float <-> monotone unsigned key (total order of the finite floats and infinities)
+static inline uint32_t f2key(float f) {
+    uint32_t b;
+    memcpy(&b, &f, 4);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+static inline float key2f(uint32_t k) {
+    uint32_t b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    float f;
+    memcpy(&f, &b, 4);
+    return f;
+}
+
+// The reference's recruitment decision for a float32 input x, in float64
+// (muscle.py:275 then pool:169-172).  `volatile` keeps the compiler from
+// contracting or re-associating the three roundings.
+static bool ref_recruited(float x, double input_scale, double thr, double min_rate) {
+    volatile double e = (double)x * input_scale;
+    volatile double d = e - thr;
+    volatile double r = d + min_rate;
+    return !(r < min_rate);
+}
+
+// Smallest float32 x with ref_recruited(x); the predicate is monotone in x.
+static float critical_input(double input_scale, double thr, double min_rate) {
+    uint32_t lo = f2key(-std::numeric_limits<float>::max());
+    uint32_t hi = f2key(std::numeric_limits<float>::infinity());
+    if (ref_recruited(key2f(lo), input_scale, thr, min_rate)) return -std::numeric_limits<float>::infinity();
+    if (!ref_recruited(key2f(hi), input_scale, thr, min_rate)) return std::numeric_limits<float>::quiet_NaN();
+    while (hi - lo > 1) {                       // invariant: lo not recruited, hi recruited
+        uint32_t mid = lo + (hi - lo) / 2;
+        if (ref_recruited(key2f(mid), input_scale, thr, min_rate)) hi = mid; else lo = mid;
+    }
+    return key2f(hi);
+}
+
+extern "C" int mb_params_pack(const MbConfig* cfg, int64_t L, const double* thr, const double* peak,
+                              const double* ptf, const double* ct, const double* fat, const double* rec,
+                              void* out_host, int32_t* table_props) {
+    if (int rc = check_cfg(cfg)) return rc;
+    if (L <= 0 || !thr || !peak || !ptf || !ct || !fat || !out_host) return fail(MB_EINVAL, "NULL table or L <= 0");
+    if (cfg->fibers_kind == MB_FIBERS_PYMUSCLE && !rec) return fail(MB_EINVAL, "rec table required for PyMuscle fibers");
+    const double rr = cfg->max_recruitment_threshold, phi = cfg->adaptation_magnitude;
+    const double minr = cfg->min_firing_rate, dd = cfg->derecruitment_delta, g = cfg->firing_gain;
+    const double ccr = cfg->contraction_time_change_ratio;
+    // A recruited unit fires at >= gain*minR, so q = phi*ratio*(r - (minR - d)) >= 0 for every
+    // recruited unit iff phi*ratio >= 0 and gain*minR clears minR - d (with float slack).
+    bool adapt_nonneg = (g * minr) * (1.0 - 1e-5) > (minr - dd);
+    for (int64_t i = 0; i < L; ++i) {
+        const double ratio = (thr[i] - 1.0) / (rr - 1.0);                 // pool:231
+        const double phir = phi * ratio;
+        const double phir6 = phir * (minr - dd);
+        adapt_nonneg = adapt_nonneg && (phir >= 0.0);
+        const double ctA = ct[i] * (1.0 + ccr) / 1000.0;
+        const double ctB = ct[i] * ccr / (1000.0 * ptf[i]);
+        const double r = rec ? rec[i] : 0.0;
+        const double rdi = r / ptf[i];
+        if (cfg->precision == MB_F32) {
+            float4* P = (float4*)out_host;
+            P[i] = make_float4(critical_input(cfg->input_scale, thr[i], minr), (float)(g * (thr[i] - minr)),
+                               (float)peak[i], (float)phir);
+            P[L + i] = make_float4((float)phir6, (float)(ctA * kKappa), (float)(ctB * kKappa), (float)fat[i]);
+            P[2 * L + i] = make_float4((float)ptf[i], (float)r, (float)rdi, (float)thr[i]);
+        } else {
+            double2* P = (double2*)out_host;
+            P[i] = make_double2(thr[i], peak[i]);
+            P[L + i] = make_double2(phir, phir6);
+            P[2 * L + i] = make_double2(ctA, ctB);
+            P[3 * L + i] = make_double2(fat[i], ptf[i]);
+            P[4 * L + i] = make_double2(r, rdi);
+        }
+    }
+    if (table_props) *table_props = adapt_nonneg ? MB_PROP_ADAPT_NONNEG : 0;
+    return MB_OK;
+}
+
+// =====================================================================================
+// K1: single step.  blockDim = (TX, TY): TY muscles per block iteration, TX threads
+// (a multiple of 32) striding over one muscle's units.  Per-muscle total = warp
+// shuffle tree + one shared-memory stage, in a fixed order (deterministic).
+// =====================================================================================
+template <typename T> struct Vec;
+template <> struct Vec<float>  { using P = float4;  using U = UnitF; using S = ScalF; };
+template <> struct Vec<double> { using P = double2; using U = UnitD; using S = ScalD; };
+
+template <typename T>
+struct K1Args {
+    const typename Vec<T>::P* params;
+    int64_t rows, L;
+    int32_t S;
+    const int32_t* seg_off;
+    const double* seg_div;
+    int32_t stage, in_per_unit, recovery, central, peripheral;
+    const T* in;
+    double* cpf;
+    double* dur;
+    T* forces;
+    T* totals;
+    uint8_t* mask;
+    T* rates;
+    double dt;
+    double adk_d;      // -log2e/tau (FP32 mode exponent scaling, applied in float64)
+    double max_dur;
+    typename Vec<T>::S sc;
+};
+
+// per-unit work, FP32 mode: float arithmetic, float64 state
+__device__ __forceinline__ float k1_unit(const K1Args<float>& a, const UnitF& p, int64_t i, float x) {
+    float fr = x;
+    if (a.stage != MB_STAGE_FIBERS) {
+        bool on;
+        float r = pool_rate_raw(p, a.sc, x, on);
+        r = on ? r : 0.0f;                                              // pool:171-172
+        fr = r;
+        if (a.central) {
+            const double d = a.dur[i];
+            fr = r - fmaxf(pool_adaptation(p, r, (float)(d * a.adk_d)), 0.0f);   // pool:221, :121
+            a.dur[i] = duration_update(d, r > 0.0f, a.dt, a.max_dur);
+        }
+        if (a.mask) a.mask[i] = on ? 1 : 0;
+        if (a.rates) a.rates[i] = fr;
+        if (a.stage == MB_STAGE_POOL) return 0.0f;
+    }
+    const double c = a.cpf[i];
+    float nf;
+    const float F = fibers_force(p, a.sc, fr, (float)c, nf);
+    if (a.forces) a.forces[i] = F;
+    if (a.peripheral) {
+        const double fatdt = (double)p.fat * a.dt, recdt = (double)p.rec * a.dt, rdidt = (double)p.rdi * a.dt;
+        a.cpf[i] = a.recovery ? fatigue_update<true>(c, (double)nf, fatdt, recdt, rdidt, (double)p.ptf)
+                              : fatigue_update<false>(c, (double)nf, fatdt, recdt, rdidt, (double)p.ptf);
+    }
+    return F;
+}
+
+// per-unit work, FP64 mode
+__device__ __forceinline__ double k1_unit(const K1Args<double>& a, const UnitD& p, int64_t i, double x) {
+    double fr = x;
+    if (a.stage != MB_STAGE_FIBERS) {
+        bool on;
+        const double r = pool_rate(p, a.sc, x, on);
+        fr = r;
+        if (a.central) {
+            const double d = a.dur[i];
+            fr = pool_adapt(p, a.sc, r, d);
+            a.dur[i] = duration_update(d, r > 0.0, a.dt, a.max_dur);
+        }
+        if (a.mask) a.mask[i] = on ? 1 : 0;
+        if (a.rates) a.rates[i] = fr;
+        if (a.stage == MB_STAGE_POOL) return 0.0;
+    }
+    const double c = a.cpf[i];
+    double nf;
+    const double F = fibers_force(p, a.sc, fr, c, nf);
+    if (a.forces) a.forces[i] = F;
+    if (a.peripheral) {
+        const double fatdt = p.fat * a.dt, recdt = p.rec * a.dt, rdidt = p.rdi * a.dt;
+        a.cpf[i] = a.recovery ? fatigue_update<true>(c, nf, fatdt, recdt, rdidt, p.ptf)
+                              : fatigue_update<false>(c, nf, fatdt, recdt, rdidt, p.ptf);
+    }
+    return F;
+}
+
+__device__ __forceinline__ float  out_scale(const ScalF& s, float v)  { return v * s.inv_out; }
+__device__ __forceinline__ double out_scale(const ScalD& s, double v) { return v / s.out_div; }   // muscle.py:278
+__device__ __forceinline__ float  out_div(float v, double d)  { return (float)((double)v / d); }
+__device__ __forceinline__ double out_div(double v, double d) { return v / d; }
+
+template <typename T>
+__global__ void __launch_bounds__(256) k1_step(const K1Args<T> a) {
+    __shared__ T red[8][8];                       // [ty][warp within the muscle's TX threads]
+    const int tx = threadIdx.x, ty = threadIdx.y, TX = blockDim.x, TY = blockDim.y;
+    const int warp_in_row = tx >> 5, warps_per_row = TX >> 5;
+    const int64_t n_muscles = a.rows * a.S;
+    for (int64_t base = (int64_t)blockIdx.x * TY; base < n_muscles; base += (int64_t)gridDim.x * TY) {
+        const int64_t mu = base + ty;
+        const bool valid = mu < n_muscles;
+        T partial = 0;
+        if (valid) {
+            const int64_t row = mu / a.S;
+            const int seg = (int)(mu - row * a.S);
+            const int off0 = a.seg_off ? a.seg_off[seg] : 0;
+            const int n = a.seg_off ? a.seg_off[seg + 1] - off0 : (int)a.L;
+            const int64_t ubase = row * a.L + off0;
+            const T xm = a.in_per_unit ? T(0) : a.in[mu];
+            for (int u = tx; u < n; u += TX) {
+                const auto p = load_unit(a.params, a.L, off0 + u);
+                const int64_t i = ubase + u;
+                const T x = a.in_per_unit ? a.in[i] : xm;
+                partial += k1_unit(a, p, i, x);
+            }
+        }
+        if (a.totals && a.stage != MB_STAGE_POOL) {          // block-uniform condition
+            partial = warp_sum(partial);
+            if ((tx & 31) == 0) red[ty][warp_in_row] = partial;
+            __syncthreads();
+            if (tx == 0 && valid) {
+                T s = red[ty][0];
+                for (int w = 1; w < warps_per_row; ++w) s += red[ty][w];
+                const int seg = (int)(mu % a.S);
+                a.totals[mu] = a.seg_div ? out_div(s, a.seg_div[seg]) : out_scale(a.sc, s);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+#include "mb_fused.cuh"
+
+// =====================================================================================
+// K3: per-muscle capacity sums (StandardMuscle.get_peripheral_fatigue, muscle.py:248-256)
+// =====================================================================================
+__global__ void __launch_bounds__(256) k3_fatigue(int64_t rows, int64_t L, int32_t S, const int32_t* seg_off,
+                                                  const double* seg_div, const double* cpf, double* out,
+                                                  double out_div) {
+    __shared__ double red[8];
+    const int64_t n_muscles = rows * S;
+    for (int64_t mu = blockIdx.x; mu < n_muscles; mu += gridDim.x) {
+        const int64_t row = mu / S;
+        const int seg = (int)(mu - row * S);
+        const int off0 = seg_off ? seg_off[seg] : 0;
+        const int n = seg_off ? seg_off[seg + 1] - off0 : (int)L;
+        double part = 0.0;
+        for (int u = threadIdx.x; u < n; u += blockDim.x) part += cpf[row * L + off0 + u];
+        part = warp_sum(part);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s = 0.0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+            out[mu] = 1.0 - s / (seg_div ? seg_div[seg] : out_div);
+        }
+        __syncthreads();
+    }
+}
+
+// =====================================================================================
+// peak probes: dependent FMA / MUFU chains, 8 independent chains per thread
+// =====================================================================================
+template <int KIND>
+__global__ void __launch_bounds__(1024) k_peak_probe(int iters, double* sink) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (KIND == 0) {
+        float v[8];
+        const float b = 1.0f - 1e-7f * (float)(t & 7), c = 1e-9f * (float)(t & 3);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 1.0f + 0.01f * (float)i;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], b, c);
+        }
+        float s = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += v[i];
+        sink[t] = (double)s;
+    } else if (KIND == 1) {
+        double v[8];
+        const double b = 1.0 - 1e-12 * (double)(t & 7), c = 1e-15 * (double)(t & 3);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 1.0 + 0.01 * (double)i;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = fma(v[i], b, c);
+        }
+        double s = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += v[i];
+        sink[t] = s;
+    } else {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.1f * (float)(i + 1) + 1e-3f * (float)(t & 15);
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = ex2_approx(-v[i]);
+        }
+        float s = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += v[i];
+        sink[t] = (double)s;
+    }
+}
+
+extern "C" int mb_peak_probe(int32_t kind, int32_t blocks, int32_t threads, int32_t iters, void* sink_dev,
+                             int64_t* lane_ops, void* stream) {
+    if (kind < 0 || kind > 2 || blocks <= 0 || threads <= 0 || threads > 1024 || iters <= 0 || !sink_dev)
+        return fail(MB_EINVAL, "mb_peak_probe: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (kind == 0) k_peak_probe<0><<<blocks, threads, 0, st>>>(iters, (double*)sink_dev);
+    else if (kind == 1) k_peak_probe<1><<<blocks, threads, 0, st>>>(iters, (double*)sink_dev);
+    else k_peak_probe<2><<<blocks, threads, 0, st>>>(iters, (double*)sink_dev);
+    MB_CUDA_OK(cudaGetLastError());
+    if (lane_ops) *lane_ops = (int64_t)blocks * threads * 64 * (int64_t)iters;
+    return MB_OK;
+}
+
+// =====================================================================================
+// launchers
+// =====================================================================================
+static int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+template <typename T>
+static int launch_k1(const MbConfig& c, const void* params, int64_t rows, int64_t L, int32_t S,
+                     const int32_t* seg_off, const double* seg_div, int32_t stage, const void* in, int32_t in_per_unit, double* cpf,
+                     double* dur, void* forces, void* totals, uint8_t* mask, void* rates, double dt,
+                     cudaStream_t st, const typename Vec<T>::S& sc) {
+    K1Args<T> a;
+    a.params = (const typename Vec<T>::P*)params;
+    a.rows = rows; a.L = L; a.S = S; a.seg_off = seg_off; a.seg_div = seg_div;
+    a.stage = stage; a.in_per_unit = in_per_unit;
+    a.recovery = c.fibers_kind == MB_FIBERS_PYMUSCLE;
+    a.central = c.central_fatigue != 0;
+    a.peripheral = c.peripheral_fatigue != 0;
+    a.in = (const T*)in; a.cpf = cpf; a.dur = dur;
+    a.forces = (T*)forces; a.totals = (T*)totals; a.mask = mask; a.rates = (T*)rates;
+    a.dt = dt;
+    a.adk_d = -kLog2e / c.adaptation_time_constant;
+    a.max_dur = c.max_duration;
+    a.sc = sc;
+    // threads per muscle: enough for the mean segment, at most 256; rows of the block = other muscles
+    const int64_t mean_n = (L + S - 1) / S;
+    int tx = (int)((mean_n + 31) / 32) * 32;
+    if (tx > 256) tx = 256;
+    if (tx < 32) tx = 32;
+    int ty = 256 / tx;
+    if (ty > 8) ty = 8;
+    const int64_t n_muscles = rows * S;
+    int64_t blocks = (n_muscles + ty - 1) / ty;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    k1_step<T><<<(unsigned)blocks, dim3(tx, ty), 0, st>>>(a);
+    MB_CUDA_OK(cudaGetLastError());
+    return MB_OK;
+}
+
+extern "C" int mb_step(const MbConfig* cfg, const void* params_dev, int64_t rows, int64_t L, int32_t S,
+                       const int32_t* seg_off_dev, const double* seg_div_dev, int32_t stage, const void* in_dev, int32_t in_per_unit,
+                       double* cpf_dev, double* dur_dev, void* forces_dev, void* totals_dev, uint8_t* mask_dev,
+                       void* rates_dev, double step_size, void* stream) {
+    if (int rc = check_cfg(cfg)) return rc;
+    if (!params_dev || !in_dev) return fail(MB_EINVAL, "mb_step: params/in is NULL");
+    if (rows <= 0 || L <= 0 || S <= 0) return fail(MB_EINVAL, "mb_step: rows, L, S must be positive");
+    if (S > 1 && !seg_off_dev) return fail(MB_EINVAL, "mb_step: seg_off required when S > 1");
+    if (stage < MB_STAGE_MUSCLE || stage > MB_STAGE_FIBERS) return fail(MB_EINVAL, "mb_step: bad stage %d", stage);
+    if (stage != MB_STAGE_POOL && !cpf_dev) return fail(MB_EINVAL, "mb_step: cpf is NULL");
+    if (stage != MB_STAGE_FIBERS && cfg->central_fatigue && !dur_dev) return fail(MB_EINVAL, "mb_step: dur is NULL");
+    if (stage == MB_STAGE_FIBERS && !in_per_unit) return fail(MB_EINVAL, "mb_step: firing rates must be per unit");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cfg->precision == MB_F32)
+        return launch_k1<float>(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, stage, in_dev, in_per_unit, cpf_dev,
+                                dur_dev, forces_dev, totals_dev, mask_dev, rates_dev, step_size, st, scal_f(*cfg));
+    return launch_k1<double>(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, stage, in_dev, in_per_unit, cpf_dev, dur_dev,
+                             forces_dev, totals_dev, mask_dev, rates_dev, step_size, st, scal_d(*cfg));
+}
+
+extern "C" int mb_peripheral_fatigue(const MbConfig* cfg, int64_t rows, int64_t L, int32_t S,
+                                     const int32_t* seg_off_dev, const double* seg_div_dev, const double* cpf_dev, double* fatigue_dev,
+                                     void* stream) {
+    if (int rc = check_cfg(cfg)) return rc;
+    if (rows <= 0 || L <= 0 || S <= 0 || !cpf_dev || !fatigue_dev) return fail(MB_EINVAL, "mb_peripheral_fatigue: bad argument");
+    if (S > 1 && !seg_off_dev) return fail(MB_EINVAL, "mb_peripheral_fatigue: seg_off required when S > 1");
+    int64_t blocks = rows * S;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    k3_fatigue<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(rows, L, S, seg_off_dev, seg_div_dev, cpf_dev,
+                                                                   fatigue_dev, cfg->output_divisor);
+    MB_CUDA_OK(cudaGetLastError());
+    return MB_OK;
+}
+
+// ---- fused geometry ---------------------------------------------------------------------
+struct FusedGeom {
+    int U, q, G, Gp, T, P, threads, smem;
+    int64_t blocks;
+};
+
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+static int fused_geometry(const MbConfig& c, int64_t M, int32_t n, int32_t K, int32_t upt, FusedGeom* g) {
+    if (n < 2 || n > 512) return fail(MB_EUNSUPPORTED, "fused kernel supports 2 <= n <= 512 units per muscle (got %d)", n);
+    if (M <= 0 || K <= 0) return fail(MB_EINVAL, "M and K must be positive");
+    const bool f32 = c.precision == MB_F32;
+    const int esz = f32 ? 4 : 8;
+    int q = 512 / n;
+    if (q < 1) q = 1;
+    if (upt != 0 && upt != 1 && upt != 2 && upt != 4) return fail(MB_EINVAL, "units_per_thread must be 0, 1, 2 or 4");
+    if (!f32 && upt == 4) return fail(MB_EINVAL, "units_per_thread 4 is FP32-only");
+    int U = upt;
+    if (U == 0) {
+        // largest U that still leaves >= 2 blocks per SM; small batches spread out instead
+        U = f32 ? 4 : 2;
+        while (U > 1 && (M + (int64_t)q * U - 1) / ((int64_t)q * U) < 2LL * sm_count()) U >>= 1;
+    }
+    // a block should not own more muscles than exist
+    while (q > 1 && (int64_t)(q - 1) * U >= M) --q;
+    g->U = U; g->q = q; g->G = q * U;
+    const int vl = 16 / esz;
+    g->Gp = (g->G + vl - 1) / vl * vl;
+    g->threads = (q * n + 31) / 32 * 32;
+    const int step_bytes = q * n * U * esz;                 // one step of the force tile
+    int T = env_int("MB_FUSED_T", 0);                        // tuning override (steps per tile)
+    if (T <= 0) {
+        T = (60 * 1024) / step_bytes;
+        if (T > 16) T = 16;
+    }
+    if (T < 1) T = 1;
+    if (T > K) T = K;
+    g->T = T;
+    // lanes per (step, q) row of the reduction: as many as fill the block once
+    int P = env_int("MB_FUSED_P", 0);
+    if (P != 1 && P != 2 && P != 4 && P != 8 && P != 16 && P != 32) {
+        P = 32;
+        while (P > 1 && (T * q * P > g->threads || P > n)) P >>= 1;
+    }
+    g->P = P;
+    g->smem = 16 + 2 * T * g->Gp * esz + T * step_bytes;
+    if (g->smem > 200 * 1024) return fail(MB_EUNSUPPORTED, "fused kernel: tile does not fit in shared memory");
+    g->blocks = (M + g->G - 1) / g->G;
+    return MB_OK;
+}
+
+extern "C" int mb_fused_geometry(const MbConfig* cfg, int64_t M, int32_t n, int32_t K, int32_t units_per_thread,
+                                 int32_t* muscles_per_block, int32_t* threads, int64_t* blocks, int32_t* smem_bytes) {
+    if (int rc = check_cfg(cfg)) return rc;
+    FusedGeom g;
+    if (int rc = fused_geometry(*cfg, M, n, K, units_per_thread, &g)) return rc;
+    if (muscles_per_block) *muscles_per_block = g.G;
+    if (threads) *threads = g.threads;
+    if (blocks) *blocks = g.blocks;
+    if (smem_bytes) *smem_bytes = g.smem;
+    return MB_OK;
+}
+
+template <typename KernelT>
+static int launch_fused(KernelT kernel, const K2Args& a, const FusedGeom& g, cudaStream_t st) {
+    if (g.smem > 48 * 1024)
+        MB_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem));
+    kernel<<<(unsigned)g.blocks, g.threads, g.smem, st>>>(a);
+    MB_CUDA_OK(cudaGetLastError());
+    return MB_OK;
+}
+
+#define MB_DISPATCH_FORCES(KERN, FIB, CEN, UU)                                                 \
+    (forces ? launch_fused(KERN<FIB, CEN, UU, true>, a, g, st) : launch_fused(KERN<FIB, CEN, UU, false>, a, g, st))
+#define MB_DISPATCH_CENTRAL(KERN, FIB, UU)                                                     \
+    (cen == 0 ? MB_DISPATCH_FORCES(KERN, FIB, 0, UU)                                           \
+              : (cen == 1 ? MB_DISPATCH_FORCES(KERN, FIB, 1, UU) : MB_DISPATCH_FORCES(KERN, FIB, 2, UU)))
+#define MB_DISPATCH_FIB(KERN, UU)                                                              \
+    (fib == MB_FIBERS_POTVIN ? MB_DISPATCH_CENTRAL(KERN, MB_FIBERS_POTVIN, UU)                  \
+                             : MB_DISPATCH_CENTRAL(KERN, MB_FIBERS_PYMUSCLE, UU))
+#define MB_DISPATCH_CENTRAL64(FIB, UU)                                                         \
+    (cen == 0 ? MB_DISPATCH_FORCES(k2_fused_f64, FIB, 0, UU) : MB_DISPATCH_FORCES(k2_fused_f64, FIB, 1, UU))
+#define MB_DISPATCH_FIB64(UU)                                                                  \
+    (fib == MB_FIBERS_POTVIN ? MB_DISPATCH_CENTRAL64(MB_FIBERS_POTVIN, UU) : MB_DISPATCH_CENTRAL64(MB_FIBERS_PYMUSCLE, UU))
+
+extern "C" int mb_step_fused(const MbConfig* cfg, const void* params_dev, int64_t M, int32_t n, int32_t K,
+                             const void* exc_dev, int64_t exc_stride_k, double* cpf_dev, double* dur_dev,
+                             void* totals_dev, int64_t totals_stride_k, void* forces_dec_dev, uint8_t* mask_dec_dev,
+                             int32_t forces_every, void* forces_last_dev, double step_size,
+                             int32_t units_per_thread, void* stream) {
+    if (int rc = check_cfg(cfg)) return rc;
+    if (!params_dev || !exc_dev || !cpf_dev) return fail(MB_EINVAL, "mb_step_fused: params/exc/cpf is NULL");
+    if (cfg->central_fatigue && !dur_dev) return fail(MB_EINVAL, "mb_step_fused: dur is NULL");
+    if (forces_every < 0 || (forces_every > 0 && !forces_dec_dev)) return fail(MB_EINVAL, "mb_step_fused: forces_every without buffer");
+    if (exc_stride_k != 0 && exc_stride_k < M) return fail(MB_EINVAL, "mb_step_fused: exc_stride_k < M");
+    if (totals_dev && totals_stride_k < M) return fail(MB_EINVAL, "mb_step_fused: totals_stride_k < M");
+    FusedGeom g;
+    if (int rc = fused_geometry(*cfg, M, n, K, units_per_thread, &g)) return rc;
+    const bool f32 = cfg->precision == MB_F32;
+    const int esz = f32 ? 4 : 8;
+
+    K2Args a;
+    memset(&a, 0, sizeof(a));
+    a.params = params_dev; a.M = M; a.n = n; a.q = g.q; a.K = K; a.T = g.T; a.P = g.P; a.G = g.G; a.Gp = g.Gp;
+    a.exc = exc_dev; a.exc_stride_k = exc_stride_k;
+    if (exc_stride_k == 0) {
+        a.exc_mode = 2;
+    } else {
+        // bulk copies need 16-byte aligned rows: base pointer, row pitch, block offset and row length
+        const bool aligned = ((uintptr_t)exc_dev % 16 == 0) && ((exc_stride_k * esz) % 16 == 0) &&
+                             ((g.G * esz) % 16 == 0) && ((M * esz) % 16 == 0);
+        a.exc_mode = (aligned && !env_int("MB_FUSED_NO_BULK", 0)) ? 0 : 1;
+    }
+    a.cpf = cpf_dev; a.dur = dur_dev; a.totals = totals_dev; a.totals_stride_k = totals_stride_k;
+    a.forces_dec = forces_dec_dev; a.mask_dec = mask_dec_dev; a.forces_every = forces_every;
+    a.forces_last = forces_last_dev;
+    a.peripheral = cfg->peripheral_fatigue != 0;
+    a.dt = step_size;
+    a.adk_d = -kLog2e / cfg->adaptation_time_constant;
+    a.max_dur = cfg->max_duration;
+    a.sf = scal_f(*cfg);
+    a.sd = scal_d(*cfg);
+
+    // central-fatigue variant (see k2_fused_f32): the fast path needs the packed table's
+    // MB_PROP_ADAPT_NONNEG guarantee and a duration clamp that exp(-dur/tau) cannot see
+    int cen = 0;
+    if (cfg->central_fatigue) {
+        const bool clamp_invisible = cfg->max_duration / cfg->adaptation_time_constant > 110.0;
+        const bool nonneg = (cfg->table_props & MB_PROP_ADAPT_NONNEG) != 0;
+        cen = (clamp_invisible && nonneg && !env_int("MB_FUSED_GENERAL", 0)) ? 1 : 2;
+    }
+    const int fib = cfg->fibers_kind;
+    const bool forces = forces_every > 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (f32) {
+        if (g.U == 4) return MB_DISPATCH_FIB(k2_fused_f32, 4);
+        if (g.U == 2) return MB_DISPATCH_FIB(k2_fused_f32, 2);
+        return MB_DISPATCH_FIB(k2_fused_f32, 1);
+    }
+    if (cen == 2) cen = 1;      // FP64 always applies both clamps (duration_update / pool_adapt)
+    if (g.U == 2) return MB_DISPATCH_FIB64(2);
+    return MB_DISPATCH_FIB64(1);
+}

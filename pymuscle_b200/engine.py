@@ -1,0 +1,270 @@
+"""
+MuscleBatch: N independent muscles advanced together on one B200.
+
+This is the batched entry point the north star adds to the reference API: the
+same ``step(excitation, step_size)`` / ``current_forces`` contract as
+``Muscle`` (pymuscle/muscle.py:61-92), but over a whole batch and with torch
+CUDA tensors.  All arithmetic happens in libmuscle_b200.so (hand-written
+sm_100a kernels behind the C ABI in include/muscle_b200.h); torch only owns
+the device memory and the stream.  There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from .tables import MuscleSpec, PackedRow, pack_row
+
+_PRECISIONS = {"f32": nat.MB_F32, "fp32": nat.MB_F32, "float32": nat.MB_F32, torch.float32: nat.MB_F32,
+               "f64": nat.MB_F64, "fp64": nat.MB_F64, "float64": nat.MB_F64, torch.float64: nat.MB_F64}
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class MuscleBatch:
+    """``batch`` rows, each holding the muscles described by ``spec``.
+
+    spec       one :class:`MuscleSpec` (uniform batch: ``batch`` identical muscles) or a
+               sequence of them (each row is that group of muscles, e.g. the 30 muscles of an arm)
+    batch      number of rows (independent copies)
+    precision  "f32" (float arithmetic, float64 state; rtol 1e-4 over 10,000 steps) or
+               "f64" (float64 throughout; rtol 1e-9).  Recruitment masks are exact in both.
+    fresh_outputs  True (default): every step returns newly allocated tensors, like the
+               reference's fresh ``current_forces`` array (fibers:258); False: reuse buffers
+    """
+
+    def __init__(self, spec: Union[MuscleSpec, Sequence[MuscleSpec]], batch: int,
+                 device: Union[str, torch.device, None] = None, precision="f32",
+                 fresh_outputs: bool = True):
+        if not torch.cuda.is_available():
+            raise RuntimeError("pymuscle_b200 needs a CUDA device: there is no CPU fallback")
+        nat.lib()
+        self.uniform = isinstance(spec, MuscleSpec)
+        specs = [spec] if self.uniform else list(spec)
+        if precision not in _PRECISIONS:
+            raise ValueError(f"precision must be 'f32' or 'f64', got {precision!r}")
+        self.precision = _PRECISIONS[precision]
+        self.dtype = torch.float32 if self.precision == nat.MB_F32 else torch.float64
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        if self.device.type != "cuda":
+            raise RuntimeError("pymuscle_b200 runs on CUDA devices only")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.rows = int(batch)
+        if self.rows <= 0:
+            raise ValueError("batch must be positive")
+        self.fresh_outputs = bool(fresh_outputs)
+
+        self.packed: PackedRow = pack_row(specs, self.precision)
+        self.specs = specs
+        self.cfg = self.packed.cfg
+        self.S, self.L = self.packed.S, self.packed.L
+        with torch.cuda.device(self.device):
+            self._params = torch.from_numpy(self.packed.blob).to(self.device)
+            self._seg_off = torch.from_numpy(self.packed.seg_off).to(self.device) if self.S > 1 else None
+            self._seg_div = torch.from_numpy(self.packed.seg_div).to(self.device) if self.S > 1 else None
+            self._ptf = torch.from_numpy(self.packed.ptf).to(self.device)
+            self.cpf = self._ptf.repeat(self.rows, 1).contiguous()            # fibers:63
+            self.dur = torch.zeros(self.rows, self.L, dtype=torch.float64, device=self.device)  # pool:79
+            self._forces = torch.zeros(self.rows, self.L, dtype=self.dtype, device=self.device)  # fibers:90
+            self._totals = torch.zeros(self.rows, self.S, dtype=self.dtype, device=self.device)
+        self.launches = 0          # kernels launched so far (bench.py reports it)
+
+    # ---- shapes ---------------------------------------------------------------------
+    @property
+    def n_muscles(self) -> int:
+        return self.rows * self.S
+
+    @property
+    def n_units(self) -> int:
+        return self.rows * self.L
+
+    @property
+    def motor_unit_count(self):
+        return self.specs[0].n if self.uniform else [s.n for s in self.specs]
+
+    @property
+    def max_excitation(self):
+        return self.specs[0].pool.max_excitation
+
+    def _shape_out(self, t: torch.Tensor) -> torch.Tensor:
+        return t.view(self.rows) if self.uniform else t
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _as_input(self, x, per_unit_ok=True):
+        """Bring an excitation argument to a contiguous device tensor of the mode's dtype.
+        Returns (tensor, per_unit)."""
+        if isinstance(x, (int, float)):
+            t = torch.full((self.rows, self.S), float(x), dtype=self.dtype, device=self.device)
+            return t, False
+        if isinstance(x, np.ndarray):
+            x = torch.from_numpy(np.ascontiguousarray(x))
+        if not isinstance(x, torch.Tensor):
+            raise TypeError(f"excitation must be a number, ndarray or torch tensor, not {type(x).__name__}")
+        t = x.to(device=self.device, dtype=self.dtype, non_blocking=True)
+        if t.numel() == self.n_muscles:
+            return t.reshape(self.rows, self.S).contiguous(), False
+        if per_unit_ok and t.numel() == self.n_units:
+            return t.reshape(self.rows, self.L).contiguous(), True
+        raise AssertionError(
+            f"excitation has {t.numel()} elements; expected {self.n_muscles} (one per muscle)"
+            + (f" or {self.n_units} (one per motor unit)" if per_unit_ok else ""))
+
+    # ---- K1: one step -----------------------------------------------------------------
+    def step(self, excitation, step_size: float, out: Optional[torch.Tensor] = None,
+             mask_out: Optional[torch.Tensor] = None, stage: int = nat.MB_STAGE_MUSCLE,
+             rates_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Advance every muscle one step (Muscle.step, muscle.py:65-92).
+
+        excitation  number, or tensor/ndarray with one value per muscle ([rows] / [rows, S]) or
+                    one per motor unit ([rows, L])
+        returns     per-muscle totals, [rows] for a uniform batch, [rows, S] otherwise
+        """
+        x, per_unit = self._as_input(excitation)
+        if stage == nat.MB_STAGE_FIBERS and not per_unit:
+            raise AssertionError("firing rates must be given per motor unit")
+        if out is None:
+            out = torch.empty(self.rows, self.S, dtype=self.dtype, device=self.device) \
+                if self.fresh_outputs else self._totals
+        else:
+            assert out.is_contiguous() and out.numel() == self.n_muscles and out.dtype == self.dtype
+        forces = None
+        if stage != nat.MB_STAGE_POOL:
+            forces = torch.empty_like(self._forces) if self.fresh_outputs else self._forces
+        if mask_out is not None:
+            assert mask_out.dtype == torch.uint8 and mask_out.numel() == self.n_units and mask_out.is_contiguous()
+        if rates_out is not None:
+            assert rates_out.dtype == self.dtype and rates_out.numel() == self.n_units and rates_out.is_contiguous()
+        with torch.cuda.device(self.device):
+            nat.check(nat.lib().mb_step(
+                C.byref(self.cfg), _ptr(self._params), self.rows, self.L, self.S,
+                _ptr(self._seg_off), _ptr(self._seg_div), stage, _ptr(x), int(per_unit),
+                _ptr(self.cpf), _ptr(self.dur), _ptr(forces),
+                _ptr(out) if stage != nat.MB_STAGE_POOL else None, _ptr(mask_out), _ptr(rates_out),
+                float(step_size), self._stream()))
+        self.launches += 1
+        if forces is not None:
+            self._forces = forces
+        return self._shape_out(out.view(self.rows, self.S))
+
+    # ---- K2: K fused steps ------------------------------------------------------------
+    def step_many(self, excitations, step_size: float, steps: Optional[int] = None,
+                  out: Optional[torch.Tensor] = None, forces_every: int = 0,
+                  return_masks: bool = False, units_per_thread: int = 0):
+        """Advance K steps in one launch with the unit state held in registers.
+
+        excitations  [K, M] (one row of per-muscle values per step) or [M] with ``steps=K``
+                     (constant over the window)
+        returns      totals [K, M]; with ``forces_every=f`` also the per-unit forces of steps
+                     f-1, 2f-1, ... as [K//f, rows, L] (and their recruitment masks if asked)
+        Falls back to K single-step launches (still on the GPU) for layouts the fused kernel
+        does not cover (ragged rows, n > 512).
+        """
+        if isinstance(excitations, np.ndarray):
+            excitations = torch.from_numpy(np.ascontiguousarray(excitations))
+        e = excitations.to(device=self.device, dtype=self.dtype, non_blocking=True).contiguous()
+        M = self.n_muscles
+        if e.dim() >= 2 and e.shape[0] * M == e.numel() and steps is None:
+            K, stride_k = int(e.shape[0]), M
+            e = e.reshape(K, M)
+        elif e.numel() == M and steps is not None:
+            K, stride_k = int(steps), 0
+            e = e.reshape(M)
+        else:
+            raise AssertionError(f"excitations must be [K, {M}] or [{M}] with steps=K (got {tuple(e.shape)})")
+        if K <= 0:
+            raise ValueError("steps must be positive")
+        if out is None:
+            out = torch.empty(K, M, dtype=self.dtype, device=self.device)
+        else:
+            assert out.is_contiguous() and out.dtype == self.dtype and tuple(out.shape) == (K, M)
+        n_dec = K // forces_every if forces_every > 0 else 0
+        forces_dec = masks = None
+        if n_dec:
+            forces_dec = torch.empty(n_dec, self.rows, self.L, dtype=self.dtype, device=self.device)
+            if return_masks:
+                masks = torch.empty(n_dec, self.rows, self.L, dtype=torch.uint8, device=self.device)
+        forces_last = torch.empty_like(self._forces) if self.fresh_outputs else self._forces
+
+        fused = self.S == 1
+        if fused:
+            try:
+                with torch.cuda.device(self.device):
+                    nat.check(nat.lib().mb_step_fused(
+                        C.byref(self.cfg), _ptr(self._params), M, self.L, K, _ptr(e), stride_k,
+                        _ptr(self.cpf), _ptr(self.dur), _ptr(out), M, _ptr(forces_dec), _ptr(masks),
+                        int(forces_every if n_dec else 0), _ptr(forces_last), float(step_size),
+                        int(units_per_thread), self._stream()))
+                self.launches += 1
+                self._forces = forces_last
+            except nat.UnsupportedError:
+                fused = False
+        if not fused:
+            keep = self.fresh_outputs
+            self.fresh_outputs = False
+            try:
+                for k in range(K):
+                    mk = masks[(k + 1) // forces_every - 1].view(-1) if (masks is not None and (k + 1) % forces_every == 0) else None
+                    self.step(e[k] if stride_k else e, step_size, out=out[k].view(self.rows, self.S), mask_out=mk)
+                    if n_dec and (k + 1) % forces_every == 0:
+                        forces_dec[(k + 1) // forces_every - 1].copy_(self._forces)
+            finally:
+                self.fresh_outputs = keep
+            if keep:
+                self._forces = self._forces.clone()
+        if n_dec:
+            return (out, forces_dec, masks) if return_masks else (out, forces_dec)
+        return out
+
+    # ---- observers --------------------------------------------------------------------
+    @property
+    def current_forces(self) -> torch.Tensor:
+        """Per-unit forces of the last step, [rows, L] (Muscle.current_forces, muscle.py:61-63)."""
+        return self._forces
+
+    @property
+    def current_peak_forces(self) -> torch.Tensor:
+        """Per-unit capacities, [rows, L] float64 (fibers:92-94)."""
+        return self.cpf
+
+    def get_peripheral_fatigue(self) -> torch.Tensor:
+        """1 - sum(capacity)/max_arb_output per muscle (StandardMuscle.get_peripheral_fatigue,
+        muscle.py:248-256), float64."""
+        out = torch.empty(self.rows, self.S, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            nat.check(nat.lib().mb_peripheral_fatigue(
+                C.byref(self.cfg), self.rows, self.L, self.S, _ptr(self._seg_off), _ptr(self._seg_div),
+                _ptr(self.cpf), _ptr(out), self._stream()))
+        self.launches += 1
+        return self._shape_out(out)
+
+    def fused_geometry(self, steps: int, units_per_thread: int = 0) -> dict:
+        mpb, thr, smem, blocks = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int64()
+        with torch.cuda.device(self.device):
+            nat.check(nat.lib().mb_fused_geometry(C.byref(self.cfg), self.n_muscles, self.L, int(steps),
+                                                  int(units_per_thread), C.byref(mpb), C.byref(thr),
+                                                  C.byref(blocks), C.byref(smem)))
+        return dict(muscles_per_block=mpb.value, threads=thr.value, blocks=blocks.value, smem_bytes=smem.value)
+
+    # ---- state ------------------------------------------------------------------------
+    def reset(self):
+        """Back to the rested state (fibers:63, pool:79)."""
+        self.cpf.copy_(self._ptf.repeat(self.rows, 1))
+        self.dur.zero_()
+        self._forces = torch.zeros_like(self._forces)
+
+    def state_dict(self) -> dict:
+        """The whole simulator state: two float64 tensors."""
+        return {"current_peak_forces": self.cpf.clone(), "recruitment_durations": self.dur.clone()}
+
+    def load_state_dict(self, state: dict):
+        self.cpf.copy_(state["current_peak_forces"].to(self.device, torch.float64).reshape(self.rows, self.L))
+        self.dur.copy_(state["recruitment_durations"].to(self.device, torch.float64).reshape(self.rows, self.L))

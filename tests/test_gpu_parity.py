@@ -1,0 +1,277 @@
+"""
+GPU parity: the CUDA path (through the C ABI, driven by MuscleBatch) against
+golden trajectories of the unmodified reference and against the oracle.
+
+Bars (BASELINE.json north_star): recruitment masks bit-exact; per-unit forces,
+capacities and totals within rtol 1e-9 (FP64 mode) / 1e-4 (FP32 mode) over
+10,000 steps.  Units do reach capacity exactly 0 and the crossing step can move
+by one between implementations, so every comparison carries a
+small absolute term next to rtol: 1e-12 x scale (FP64) / 1e-6 x scale (FP32),
+scale = the unit's peak twitch force (per-unit values) or the muscle's maximal
+output (totals).
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, trajectory_names, traj_kwargs
+from oracle.pymuscle_oracle import OracleMuscles, PoolHyper, UnitTables, recruitment_mask
+from pymuscle_b200 import MuscleBatch, MuscleSpec
+from pymuscle_b200 import _native as nat
+
+pytestmark = pytest.mark.gpu
+
+RTOL = {"f32": 1e-4, "f64": 1e-9}
+ATOL_REL = {"f32": 1e-6, "f64": 1e-12}
+STD_FORCE_FOR_N = {120: 32.0, 340: 90.0, 2000: 527.1}
+
+
+def make_spec(kind, n, kw):
+    if kind == "potvin":
+        return MuscleSpec.potvin(n, **kw)
+    spec = MuscleSpec.standard(STD_FORCE_FOR_N[n], **kw)
+    assert spec.n == n
+    return spec
+
+
+def close(got, want, precision, scale, what):
+    got = np.asarray(got, dtype=np.float64)
+    err = np.abs(got - want)
+    bound = RTOL[precision] * np.abs(want) + ATOL_REL[precision] * scale
+    bad = err > bound
+    assert not bad.any(), (f"{what}: {bad.sum()} of {bad.size} outside tolerance; worst excess "
+                           f"{(err - bound).max():.3e}, worst rel {np.max(err / np.maximum(np.abs(want), 1e-300)):.3e}")
+
+
+def total_scale(spec):
+    return float(np.sum(spec.tables()["ptf"])) / spec.output_divisor
+
+
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+@pytest.mark.parametrize("mode", ["single_step", "fused"])
+@pytest.mark.parametrize("name", trajectory_names())
+def test_trajectory(cuda_device, name, mode, precision):
+    g = golden("traj_" + name)
+    exc, dt, n, kind = g["exc"], float(g["dt"]), int(g["n"]), str(g["kind"])
+    per_unit = bool(g["per_unit"])
+    if per_unit and mode == "fused":
+        pytest.skip("per-unit excitation vectors are a single-step feature")
+    K, m = exc.shape[:2]
+    spec = make_spec(kind, n, traj_kwargs(g))
+    ptf = spec.tables()["ptf"]
+    b = MuscleBatch(spec, m, cuda_device, precision)
+    x = torch.from_numpy(exc).to(cuda_device, b.dtype)
+    totals = torch.empty(K, m, dtype=b.dtype, device=cuda_device)
+    prev = 0
+    cps = [int(c) for c in g["checkpoints"]]
+    for i, cp in enumerate(cps + ([K - 1] if cps[-1] != K - 1 else [])):
+        if mode == "single_step":
+            for k in range(prev, cp + 1):
+                totals[k] = b.step(x[k], dt)
+        else:
+            totals[prev:cp + 1] = b.step_many(x[prev:cp + 1], dt)
+        prev = cp + 1
+        if i < len(cps):
+            close(b.current_forces.cpu().numpy(), g["forces"][i], precision, ptf, f"forces@{cp}")
+            close(b.cpf.cpu().numpy(), g["cpf"][i], precision, ptf, f"capacities@{cp}")
+            np.testing.assert_allclose(b.dur.cpu().numpy(), g["dur"][i], rtol=1e-9, atol=1e-12)
+    close(totals.cpu().numpy(), g["totals"], precision, total_scale(spec), "totals")
+
+
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_recruitment_mask_probes(cuda_device, precision):
+    """Inputs within a few ulps of every threshold: the mask must be the reference's, bit for bit."""
+    g = golden("mask_probes")
+    cases = [("probes32", "mask32", MuscleSpec.potvin(120)), ("xprobes32", "xmask32", MuscleSpec.standard())]
+    if precision == "f64":
+        cases.append(("probes64", "mask64", MuscleSpec.potvin(120)))
+    for pk, mk, spec in cases:
+        probes = g[pk]
+        want = np.unpackbits(g[mk], axis=1)[:, :120]
+        b = MuscleBatch(spec, len(probes), cuda_device, precision)
+        mask = torch.empty(len(probes), 120, dtype=torch.uint8, device=cuda_device)
+        b.step(torch.from_numpy(probes.astype(np.float64)).to(cuda_device, b.dtype), 0.02, mask_out=mask)
+        assert np.array_equal(mask.cpu().numpy(), want), pk
+        # per-unit form of the same inputs
+        b = MuscleBatch(spec, len(probes), cuda_device, precision)
+        xu = torch.from_numpy(np.repeat(probes.astype(np.float64)[:, None], 120, axis=1)).to(cuda_device, b.dtype)
+        b.step(xu, 0.02, mask_out=mask)
+        assert np.array_equal(mask.cpu().numpy(), want), pk + " per-unit"
+
+
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+@pytest.mark.parametrize("kind", ["potvin", "standard"])
+def test_masks_random_excitation_fused_and_single(cuda_device, kind, precision):
+    rng = np.random.default_rng(11)
+    m, K, n = 37, 64, 120
+    spec = MuscleSpec.potvin(n) if kind == "potvin" else MuscleSpec.standard()
+    exc = (rng.random((K, m)) * (67.0 if kind == "potvin" else 1.0)).astype(np.float32)
+    t, h = UnitTables.build(n), PoolHyper()
+    e64 = exc.astype(np.float64)[:, :, None] * spec.input_scale
+    want = recruitment_mask(np.broadcast_to(e64, (K, m, n)), t, h).astype(np.uint8)
+    b = MuscleBatch(spec, m, cuda_device, precision)
+    x = torch.from_numpy(exc).to(cuda_device, b.dtype)
+    _, _, masks = b.step_many(x, 0.02, forces_every=1, return_masks=True)
+    assert np.array_equal(masks.cpu().numpy(), want)
+    b = MuscleBatch(spec, m, cuda_device, precision)
+    mask = torch.empty(m, n, dtype=torch.uint8, device=cuda_device)
+    for k in range(K):
+        b.step(x[k], 0.02, mask_out=mask)
+        assert np.array_equal(mask.cpu().numpy(), want[k])
+
+
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_fused_equals_single_step_and_decimated_forces(cuda_device, precision):
+    """K2 against K1 on the same inputs, odd sizes: M not a multiple of the block's muscle
+    count, K not a multiple of the tile, windows of different lengths."""
+    rng = np.random.default_rng(5)
+    m, n = 203, 120
+    spec = MuscleSpec.standard()
+    exc = rng.random((97, m)).astype(np.float32)
+    ptf = spec.tables()["ptf"]
+    a = MuscleBatch(spec, m, cuda_device, precision)
+    b = MuscleBatch(spec, m, cuda_device, precision)
+    x = torch.from_numpy(exc).to(cuda_device, a.dtype)
+    t1 = torch.stack([a.step(x[k], 0.02) for k in range(97)])
+    f1_at = {}
+    t2a, fdec = b.step_many(x[:60], 0.02, forces_every=7)
+    t2b = b.step_many(x[60:], 0.02)
+    close(torch.cat([t2a, t2b]).cpu().numpy(), t1.double().cpu().numpy(), precision, total_scale(spec), "totals")
+    close(b.cpf.cpu().numpy(), a.cpf.cpu().numpy(), precision, ptf, "capacities")
+    close(b.current_forces.cpu().numpy(), a.current_forces.double().cpu().numpy(), precision, ptf, "forces")
+    assert fdec.shape == (60 // 7, m, n)
+    c = MuscleBatch(spec, m, cuda_device, precision)
+    for k in range(56):
+        c.step(x[k], 0.02)
+        if (k + 1) % 7 == 0:
+            close(fdec[(k + 1) // 7 - 1].cpu().numpy(), c.current_forces.double().cpu().numpy(), precision, ptf, f"dec{k}")
+
+
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+@pytest.mark.parametrize("upt", [1, 2, 4])
+def test_fused_units_per_thread_variants(cuda_device, precision, upt):
+    if precision == "f64" and upt == 4:
+        pytest.skip("4 units per thread is FP32-only")
+    rng = np.random.default_rng(upt)
+    m, n, K = 70, 120, 40
+    exc = (67.0 * rng.random((K, m))).astype(np.float32)
+    ora = OracleMuscles(n, m, "potvin")
+    want = np.stack([ora.step(exc[k].astype(np.float64), 0.02).total for k in range(K)])
+    b = MuscleBatch(MuscleSpec.potvin(n), m, cuda_device, precision)
+    got = b.step_many(torch.from_numpy(exc).to(cuda_device, b.dtype), 0.02, units_per_thread=upt)
+    close(got.cpu().numpy(), want, precision, 2609.03, "totals")
+    close(b.cpf.cpu().numpy(), ora.cpf, precision, ora.t.ptf, "capacities")
+    np.testing.assert_allclose(b.dur.cpu().numpy(), ora.dur, rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_fused_constant_excitation_and_unaligned_batch(cuda_device, precision):
+    """exc_stride_k == 0 (one value per muscle for the window) and M % 4 != 0 (no bulk copies)."""
+    rng = np.random.default_rng(8)
+    for m in (64, 61):
+        e = (67.0 * rng.random(m)).astype(np.float32)
+        ora = OracleMuscles(120, m, "potvin")
+        want = np.stack([ora.step(e.astype(np.float64), 0.02).total for _ in range(50)])
+        b = MuscleBatch(MuscleSpec.potvin(120), m, cuda_device, precision)
+        got = b.step_many(torch.from_numpy(e).to(cuda_device, b.dtype), 0.02, steps=50)
+        close(got.cpu().numpy(), want, precision, 2609.03, f"const m={m}")
+        b = MuscleBatch(MuscleSpec.potvin(120), m, cuda_device, precision)
+        full = torch.from_numpy(np.repeat(e[None], 50, 0)).to(cuda_device, b.dtype)
+        got = b.step_many(full, 0.02)
+        close(got.cpu().numpy(), want, precision, 2609.03, f"per-step m={m}")
+
+
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_halves_pool_and_fibers_stages(cuda_device, precision):
+    """Pool.step and Fibers.step on their own (stage POOL / stage FIBERS of mb_step)."""
+    g = golden("halves")
+    n = 120
+    b = MuscleBatch(MuscleSpec.potvin(n), 1, cuda_device, precision)
+    rates = torch.empty(1, n, dtype=b.dtype, device=cuda_device)
+    for e, want in zip(g["pool_exc"], g["pool_rates"]):
+        b.step(torch.from_numpy(e.astype(np.float64)).to(cuda_device, b.dtype), 0.5, stage=nat.MB_STAGE_POOL, rates_out=rates)
+        close(rates[0].cpu().numpy(), want, precision, 35.0, "rates")
+    np.testing.assert_allclose(b.dur[0].cpu().numpy(), g["pool_dur"], rtol=1e-12)
+    for name, spec in (("fib", MuscleSpec.potvin(n)), ("pmf", MuscleSpec(n, fibers=MuscleSpec.standard().fibers))):
+        b = MuscleBatch(spec, 1, cuda_device, precision)
+        ptf = spec.tables()["ptf"]
+        for r, want in zip(g[f"{name}_rates"], g[f"{name}_totals"]):
+            tot = b.step(torch.from_numpy(r.astype(np.float64)).to(cuda_device, b.dtype), 0.5, stage=nat.MB_STAGE_FIBERS)
+            close(tot.cpu().numpy(), [want], precision, 2609.03, name + " total")
+        close(b.cpf[0].cpu().numpy(), g[f"{name}_cpf"], precision, ptf, name + " cpf")
+        close(b.current_forces[0].cpu().numpy(), g[f"{name}_forces_last"], precision, ptf, name + " forces")
+
+
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_arm_ragged_rows(cuda_device, precision):
+    """BASELINE config #3 shape: 30 StandardMuscles of 256..3127 units per row (35,032 units)."""
+    g = golden("arm")
+    specs = [MuscleSpec.standard(max_force=float(f)) for f in g["max_forces"]]
+    assert [s.n for s in specs] == list(g["counts"])
+    rows = 3
+    b = MuscleBatch(specs, rows, cuda_device, precision)
+    assert b.L == 35032 and b.S == 30
+    ptf = np.concatenate([s.tables()["ptf"] for s in specs])
+    for k in range(g["exc"].shape[0]):
+        x = torch.from_numpy(np.repeat(g["exc"][k][None], rows, 0)).to(cuda_device, b.dtype)
+        tot = b.step(x, float(g["dt"]))
+        for r in range(rows):
+            close(tot[r].cpu().numpy(), g["totals"][k], precision, 1.0, f"arm totals step {k}")
+    for r in range(rows):
+        close(b.cpf[r].cpu().numpy(), g["cpf"], precision, ptf, "arm capacities")
+        close(b.current_forces[r].cpu().numpy(), g["forces"], precision, ptf, "arm forces")
+    fat = b.get_peripheral_fatigue()
+    want = np.array([1 - sum(g["cpf"][o:o + s.n]) / s.output_divisor
+                     for o, s in zip(np.cumsum([0] + [s.n for s in specs[:-1]]), specs)])
+    np.testing.assert_allclose(fat[0].cpu().numpy(), want, rtol=1e-6, atol=1e-9)
+
+
+def test_full_size_properties_config2(cuda_device):
+    """BASELINE config #2 at full size (65,536 x 120, fused 1,000 steps, FP32 mode), checked
+    through size-independent properties: (i) muscles given the same excitation produce the
+    same output wherever they sit in the batch; (ii) a sample of muscles matches the oracle;
+    (iii) capacities never increase for Potvin fibers and stay in [0, peak]; (iv) zero
+    excitation leaves the state untouched."""
+    M, n, K, dt = 65536, 120, 1000, 0.02
+    rng = np.random.default_rng(2017)
+    levels = (67.0 * rng.random(64)).astype(np.float32)
+    levels[0] = 0.0
+    idx = rng.integers(0, 64, size=M)
+    idx[:64] = np.arange(64)
+    e = torch.from_numpy(levels[idx]).to(cuda_device)
+    b = MuscleBatch(MuscleSpec.potvin(n), M, cuda_device, "f32")
+    tot = b.step_many(e, dt, steps=K)
+    torch.cuda.synchronize()
+    tot = tot.cpu().numpy()
+    cpf = b.cpf.cpu().numpy()
+    for lv in range(64):                                   # (i)
+        cols = np.nonzero(idx == lv)[0]
+        assert np.array_equal(tot[:, cols], np.repeat(tot[:, cols[:1]], len(cols), 1))
+        assert np.array_equal(cpf[cols], np.repeat(cpf[cols[:1]], len(cols), 0))
+    ora = OracleMuscles(n, 64, "potvin")                   # (ii)
+    want = np.stack([ora.step(levels.astype(np.float64), dt).total for _ in range(K)])
+    close(tot[:, :64], want, "f32", 2609.03, "sampled totals")
+    close(cpf[:64], ora.cpf, "f32", ora.t.ptf, "sampled capacities")
+    assert (cpf <= ora.t.ptf[None] * (1 + 1e-7)).all() and (cpf >= 0).all()      # (iii)
+    zero = np.nonzero(idx == 0)[0]                          # (iv)
+    assert np.array_equal(cpf[zero], np.repeat(ora.t.ptf[None], len(zero), 0))
+    assert (tot[:, zero] == 0).all() and (b.dur.cpu().numpy()[zero] == 0).all()
+
+
+def test_state_dict_roundtrip_and_fresh_outputs(cuda_device):
+    spec = MuscleSpec.standard()
+    a = MuscleBatch(spec, 16, cuda_device, "f64")
+    x = torch.rand(16, device=cuda_device, dtype=torch.float64)
+    f_prev = None
+    for _ in range(10):
+        a.step(x, 0.1)
+        f = a.current_forces
+        assert f_prev is None or f.data_ptr() != f_prev.data_ptr()      # fresh array per step (fibers:258)
+        f_prev = f
+    st = a.state_dict()
+    b = MuscleBatch(spec, 16, cuda_device, "f64")
+    b.load_state_dict(st)
+    assert torch.equal(a.step(x, 0.1), b.step(x, 0.1))
+    assert torch.equal(a.cpf, b.cpf)
+    b.reset()
+    assert torch.equal(b.cpf[0], torch.from_numpy(spec.tables()["ptf"]).to(cuda_device))

@@ -1,0 +1,125 @@
+"""
+CPU-side checks of the C ABI: the shared library loads, exports every symbol
+include/muscle_b200.h declares, and its host-side functions (parameter packing,
+launch geometry, argument validation) behave.  No kernel is launched here.
+"""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden
+from oracle.pymuscle_oracle import PoolHyper, UnitTables, recruitment_mask
+from pymuscle_b200 import _native as nat
+from pymuscle_b200.tables import MuscleSpec, force_to_motor_unit_count, pack_row
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "muscle_b200.h")).read()
+    declared = set(re.findall(r"\b(mb_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(nat.SYMBOLS)
+    lib = nat.lib()
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.mb_abi_version() == nat.ABI_VERSION
+
+
+def test_config_struct_layout_matches_header():
+    # 4 int32 + 10 double + 2 int32
+    assert C.sizeof(nat.MbConfig) == 4 * 4 + 10 * 8 + 2 * 4
+
+
+def test_tables_bit_identical_to_reference():
+    g = golden("tables")
+    for n in (2, 33, 120, 340, 2000):
+        t = MuscleSpec(n, fibers=MuscleSpec.standard().fibers).tables()
+        for key in ("thr", "peak", "ptf", "ct", "fat", "rec"):
+            assert np.array_equal(t[key], g[f"{key}_{n}"]), (key, n)
+    for mf, cnt in g["counts_for_force"]:
+        assert force_to_motor_unit_count(float(mf), 0.0123) == int(cnt)
+    assert MuscleSpec.standard().output_divisor == float(g["max_arb_output_120"])
+    assert MuscleSpec.standard().input_scale == 67.0
+
+
+@pytest.mark.parametrize("kind", ["potvin", "standard"])
+def test_pack_f32_critical_inputs_reproduce_the_float64_predicate(kind):
+    """crit[i] is the smallest float32 input the reference recruits unit i for."""
+    spec = MuscleSpec.potvin(120) if kind == "potvin" else MuscleSpec.standard()
+    row = pack_row([spec], nat.MB_F32)
+    P = row.blob.view(np.float32).reshape(3, 120, 4)
+    crit = P[0, :, 0]
+    t, h = UnitTables.build(120), PoolHyper()
+    scale = spec.input_scale
+    for c_i, i in zip(crit, range(120)):
+        below = np.nextafter(c_i, np.float32(-np.inf))
+        on = recruitment_mask(np.float64(c_i) * scale, t, h)[i]
+        off = recruitment_mask(np.float64(below) * scale, t, h)[i]
+        assert on and not off
+    # the packed float tables are the float64 tables rounded once
+    tab = spec.tables()
+    np.testing.assert_array_equal(P[0, :, 2], tab["peak"].astype(np.float32))
+    np.testing.assert_array_equal(P[1, :, 3], tab["fat"].astype(np.float32))
+    np.testing.assert_array_equal(P[2, :, 0], tab["ptf"].astype(np.float32))
+    assert row.cfg.table_props & nat.MB_PROP_ADAPT_NONNEG
+
+
+def test_pack_f64_layout():
+    spec = MuscleSpec.standard()
+    row = pack_row([spec], nat.MB_F64)
+    P = row.blob.view(np.float64).reshape(5, 120, 2)
+    tab = spec.tables()
+    np.testing.assert_array_equal(P[0, :, 0], tab["thr"])
+    np.testing.assert_array_equal(P[0, :, 1], tab["peak"])
+    np.testing.assert_array_equal(P[3, :, 0], tab["fat"])
+    np.testing.assert_array_equal(P[3, :, 1], tab["ptf"])
+    np.testing.assert_array_equal(P[4, :, 0], tab["rec"])
+    np.testing.assert_allclose(P[2, :, 0], tab["ct"] * 1.379 / 1000, rtol=1e-15)
+
+
+def test_pack_ragged_row():
+    specs = [MuscleSpec.standard(max_force=f) for f in (68.0, 90.0, 120.0)]
+    row = pack_row(specs, nat.MB_F32)
+    assert list(row.seg_off) == [0, specs[0].n, specs[0].n + specs[1].n, sum(s.n for s in specs)]
+    assert row.L == sum(s.n for s in specs)
+    np.testing.assert_array_equal(row.seg_div, [s.output_divisor for s in specs])
+    with pytest.raises(ValueError):
+        pack_row([MuscleSpec.standard(), MuscleSpec.potvin(120)], nat.MB_F32)
+
+
+def test_argument_validation_without_a_gpu():
+    lib = nat.lib()
+    cfg = pack_row([MuscleSpec.potvin(120)], nat.MB_F32).cfg
+    rc = lib.mb_step(C.byref(cfg), None, 1, 120, 1, None, None, 0, None, 0, None, None, None, None, None, None, 0.02, None)
+    assert rc == nat.MB_EINVAL and b"NULL" in lib.mb_last_error()
+    with pytest.raises(nat.NativeError):
+        nat.check(rc)
+    bad = nat.MbConfig()
+    C.memmove(C.byref(bad), C.byref(cfg), C.sizeof(cfg))
+    bad.precision = 7
+    assert lib.mb_params_bytes(C.byref(bad), 120) > 0
+    assert lib.mb_params_pack(C.byref(bad), 120, None, None, None, None, None, None, None, None) == nat.MB_EINVAL
+    # fused kernel range
+    mpb, thr, smem, blocks = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int64()
+    rc = lib.mb_fused_geometry(C.byref(cfg), 65536, 2000, 1000, 0, C.byref(mpb), C.byref(thr), C.byref(blocks), C.byref(smem))
+    assert rc == nat.MB_EUNSUPPORTED
+    with pytest.raises(nat.UnsupportedError):
+        nat.check(rc)
+
+
+def test_fused_geometry_for_the_headline_config():
+    lib = nat.lib()
+    cfg = pack_row([MuscleSpec.potvin(120)], nat.MB_F32).cfg
+    mpb, thr, smem, blocks = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int64()
+    nat.check(lib.mb_fused_geometry(C.byref(cfg), 65536, 120, 1000, 0, C.byref(mpb), C.byref(thr),
+                                    C.byref(blocks), C.byref(smem)))
+    assert thr.value == 480 and mpb.value == 16 and blocks.value == 4096
+    assert smem.value <= 100 * 1024
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    monkeypatch.setattr(nat, "_lib", None)
+    monkeypatch.setattr(nat, "LIB_PATH", "/nonexistent/libmuscle_b200.so")
+    with pytest.raises(ImportError, match="no CPU fallback"):
+        nat.lib()
