@@ -28,7 +28,8 @@ struct UnitF {
     float fat;     // nominal fatigability                                             (fibers:110)
     float ptf;     // peak twitch force (upper clamp)                                  (pmf:104-105)
     float rec;     // recovery rate                                                    (pmf:140)
-    float rdi;     // rec / ptf:  recovery = (rec - rdi*cpf) * dt                      (pmf:137-140)
+    float rdi;     // rec / ptf:  recovery = (ptf - cpf) * rdi * dt                    (pmf:137-140)
+    float ptf_lo;  // ptf - (float)ptf, so that ptf + ptf_lo carries 48 bits of the float64 peak
 };
 
 struct UnitD {
@@ -40,7 +41,7 @@ __device__ __forceinline__ UnitF load_unit(const float4* __restrict__ P, int64_t
     UnitF u;
     u.crit = a.x; u.thr_g = a.y; u.peak = a.z; u.phir = a.w;
     u.phir6 = b.x; u.ctA = b.y; u.ctB = b.z; u.fat = b.w;
-    u.ptf = c.x; u.rec = c.y; u.rdi = c.z;
+    u.ptf = c.x; u.rec = c.y; u.rdi = c.z; u.ptf_lo = c.w;
     return u;
 }
 
@@ -143,13 +144,14 @@ __device__ __forceinline__ double fibers_force(const UnitD& p, const ScalD& s, d
 }
 
 // Capacity update, float64 state (used by K1 in both modes and by K2 in FP64 mode).
-// fatdt = fat*dt, recdt = rec*dt, rdidt = rdi*dt (all zero when peripheral fatigue is off).
+// fatdt = fat*dt, rdidt = (rec/ptf)*dt (both zero when peripheral fatigue is off).  The
+// recovery term is written (ptf - c) * rdidt so that it is exactly 0 for a rested unit,
+// as in the reference's rec * ((ptf - c)/ptf) * dt.
 template <bool RECOVERY>
-__device__ __forceinline__ double fatigue_update(double cpf, double nf, double fatdt, double recdt,
-                                                 double rdidt, double ptf) {
+__device__ __forceinline__ double fatigue_update(double cpf, double nf, double fatdt, double rdidt, double ptf) {
     double c = fma(-nf, fatdt, cpf);                                    // fibers:110-111
     if (RECOVERY) {
-        if (nf <= 0.0) c += fma(-c, rdidt, recdt);                      // pmf:121-141
+        if (nf <= 0.0) c = fma(ptf - c, rdidt, c);                      // pmf:121-141
     }
     c = (c < 0.0) ? 0.0 : c;                                            // fibers:114
     if (RECOVERY) c = (c > ptf) ? ptf : c;                              // pmf:104-105

@@ -219,7 +219,6 @@ __global__ void __launch_bounds__(512, 2) k2_fused_f32(const K2Args a) {
     const UnitF p = load_unit((const float4*)a.params, n, u);
     const ScalF sc = a.sf;
     const float fatdt = a.peripheral ? (float)((double)p.fat * a.dt) : 0.0f;
-    const float recdt = a.peripheral ? (float)((double)p.rec * a.dt) : 0.0f;
     const float rdidt = a.peripheral ? (float)((double)p.rdi * a.dt) : 0.0f;
     const float dtk = (float)(a.dt * a.adk_d);
 
@@ -235,7 +234,7 @@ __global__ void __launch_bounds__(512, 2) k2_fused_f32(const K2Args a) {
         hi[j] = (float)c;
         lo[j] = (float)(c - (double)hi[j]);
         cpf[j] = hi[j] + lo[j];
-        room[j] = p.ptf - hi[j];
+        room[j] = (p.ptf - hi[j]) + p.ptf_lo;            // peak - hi: the upper bound of lo (pmf:104-105)
         cnt[j] = 0.0f;
         arg0[j] = (float)(d0 * a.adk_d);
         F[j] = 0.0f;
@@ -297,8 +296,8 @@ __global__ void __launch_bounds__(512, 2) k2_fused_f32(const K2Args a) {
                     // capacity update on the compensated pair (fibers:110-114, pmf:94-105)
                     float l = fmaf(nf, -fatdt, lo[j]);
                     if (FIB == MB_FIBERS_PYMUSCLE) {
-                        const float rcv = fmaf(cpf[j], -rdidt, recdt);
-                        l += (nf <= 0.0f) ? rcv : 0.0f;
+                        const float gap = room[j] - lo[j];                 // peak - capacity
+                        l = fmaf((nf <= 0.0f) ? gap : 0.0f, rdidt, l);     // pmf:121-141
                     }
                     l = fmaxf(l, -hi[j]);
                     if (FIB == MB_FIBERS_PYMUSCLE) l = fminf(l, room[j]);
@@ -315,7 +314,7 @@ __global__ void __launch_bounds__(512, 2) k2_fused_f32(const K2Args a) {
                 const float err = (hi[j] - (s1 - bb)) + (lo[j] - bb);
                 hi[j] = s1;
                 lo[j] = err;
-                room[j] = p.ptf - s1;
+                room[j] = (p.ptf - s1) + p.ptf_lo;
             }
         }
         __syncthreads();                                   // force tile complete
@@ -327,7 +326,14 @@ __global__ void __launch_bounds__(512, 2) k2_fused_f32(const K2Args a) {
     for (int j = 0; j < U; ++j) {
         if (!valid[j]) continue;
         const int64_t idx = (m0 + tq * U + j) * n + u;
-        if (a.peripheral) a.cpf[idx] = (double)hi[j] + (double)lo[j];
+        if (a.peripheral) {
+            // add the window's change to the float64 state: an untouched unit keeps its
+            // exact bits, and the low bits of the incoming capacity are not truncated
+            const double c0 = a.cpf[idx];
+            const float h0 = (float)c0;
+            const float l0 = (float)(c0 - (double)h0);
+            a.cpf[idx] = c0 + (((double)hi[j] - (double)h0) + ((double)lo[j] - (double)l0));
+        }
         if (CENTRAL) {
             double d = fma((double)cnt[j], a.dt, a.dur[idx]);
             d = (d > a.max_dur) ? a.max_dur : d;
@@ -360,7 +366,6 @@ __global__ void __launch_bounds__(512, 1) k2_fused_f64(const K2Args a) {
     const UnitD p = load_unit((const double2*)a.params, n, u);
     const ScalD sc = a.sd;
     const double fatdt = a.peripheral ? p.fat * a.dt : 0.0;
-    const double recdt = a.peripheral ? p.rec * a.dt : 0.0;
     const double rdidt = a.peripheral ? p.rdi * a.dt : 0.0;
 
     double cpf[U], dur[U], F[U];
@@ -417,7 +422,7 @@ __global__ void __launch_bounds__(512, 1) k2_fused_f64(const K2Args a) {
                             if (a.mask_dec) a.mask_dec[idx] = on ? 1 : 0;
                         }
                     }
-                    cpf[j] = fatigue_update<FIB == MB_FIBERS_PYMUSCLE>(cpf[j], nf, fatdt, recdt, rdidt, p.ptf);
+                    cpf[j] = fatigue_update<FIB == MB_FIBERS_PYMUSCLE>(cpf[j], nf, fatdt, rdidt, p.ptf);
                 }
                 *fp = fv;
             }

@@ -148,7 +148,7 @@ extern "C" int mb_params_pack(const MbConfig* cfg, int64_t L, const double* thr,
             P[i] = make_float4(critical_input(cfg->input_scale, thr[i], minr), (float)(g * (thr[i] - minr)),
                                (float)peak[i], (float)phir);
             P[L + i] = make_float4((float)phir6, (float)(ctA * kKappa), (float)(ctB * kKappa), (float)fat[i]);
-            P[2 * L + i] = make_float4((float)ptf[i], (float)r, (float)rdi, (float)thr[i]);
+            P[2 * L + i] = make_float4((float)ptf[i], (float)r, (float)rdi, (float)(ptf[i] - (double)(float)ptf[i]));
         } else {
             double2* P = (double2*)out_host;
             P[i] = make_double2(thr[i], peak[i]);
@@ -214,9 +214,10 @@ __device__ __forceinline__ float k1_unit(const K1Args<float>& a, const UnitF& p,
     const float F = fibers_force(p, a.sc, fr, (float)c, nf);
     if (a.forces) a.forces[i] = F;
     if (a.peripheral) {
-        const double fatdt = (double)p.fat * a.dt, recdt = (double)p.rec * a.dt, rdidt = (double)p.rdi * a.dt;
-        a.cpf[i] = a.recovery ? fatigue_update<true>(c, (double)nf, fatdt, recdt, rdidt, (double)p.ptf)
-                              : fatigue_update<false>(c, (double)nf, fatdt, recdt, rdidt, (double)p.ptf);
+        const double fatdt = (double)p.fat * a.dt, rdidt = (double)p.rdi * a.dt;
+        const double ptf = (double)p.ptf + (double)p.ptf_lo;
+        a.cpf[i] = a.recovery ? fatigue_update<true>(c, (double)nf, fatdt, rdidt, ptf)
+                              : fatigue_update<false>(c, (double)nf, fatdt, rdidt, ptf);
     }
     return F;
 }
@@ -242,9 +243,9 @@ __device__ __forceinline__ double k1_unit(const K1Args<double>& a, const UnitD& 
     const double F = fibers_force(p, a.sc, fr, c, nf);
     if (a.forces) a.forces[i] = F;
     if (a.peripheral) {
-        const double fatdt = p.fat * a.dt, recdt = p.rec * a.dt, rdidt = p.rdi * a.dt;
-        a.cpf[i] = a.recovery ? fatigue_update<true>(c, nf, fatdt, recdt, rdidt, p.ptf)
-                              : fatigue_update<false>(c, nf, fatdt, recdt, rdidt, p.ptf);
+        const double fatdt = p.fat * a.dt, rdidt = p.rdi * a.dt;
+        a.cpf[i] = a.recovery ? fatigue_update<true>(c, nf, fatdt, rdidt, p.ptf)
+                              : fatigue_update<false>(c, nf, fatdt, rdidt, p.ptf);
     }
     return F;
 }

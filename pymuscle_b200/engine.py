@@ -224,6 +224,53 @@ class MuscleBatch:
             return (out, forces_dec, masks) if return_masks else (out, forces_dec)
         return out
 
+    # ---- K2 with host buffers: H2D / compute / D2H pipelined over sub-windows ---------
+    def step_many_host(self, exc_host: torch.Tensor, step_size: float, out_host: torch.Tensor,
+                       chunk: int = 125) -> torch.Tensor:
+        """``step_many`` for excitations and totals that live in (pinned) HOST memory.
+
+        The window is cut into sub-windows of ``chunk`` steps; the host->device copy of
+        sub-window i+1, the fused kernel of sub-window i and the device->host copy of
+        sub-window i-1 run concurrently on three streams (double-buffered staging), so the
+        call costs max(PCIe, kernel) rather than their sum.  Returns ``out_host``; the
+        caller's current stream is made to wait for the last copy.
+        """
+        K, M = int(exc_host.shape[0]), self.n_muscles
+        assert exc_host.device.type == "cpu" and out_host.device.type == "cpu"
+        assert tuple(exc_host.shape) == (K, M) and tuple(out_host.shape) == (K, M)
+        assert exc_host.dtype == self.dtype and out_host.dtype == self.dtype
+        chunk = max(1, min(int(chunk), K))
+        st = getattr(self, "_host_pipe", None)
+        if st is None or st["chunk"] != chunk:
+            with torch.cuda.device(self.device):
+                st = dict(chunk=chunk, h2d=torch.cuda.Stream(self.device), d2h=torch.cuda.Stream(self.device),
+                          exc=[torch.empty(chunk, M, dtype=self.dtype, device=self.device) for _ in range(2)],
+                          tot=[torch.empty(chunk, M, dtype=self.dtype, device=self.device) for _ in range(2)],
+                          up=[torch.cuda.Event() for _ in range(2)], run=[torch.cuda.Event() for _ in range(2)],
+                          down=[torch.cuda.Event() for _ in range(2)])
+            self._host_pipe = st
+        cur = torch.cuda.current_stream(self.device)
+        st["h2d"].wait_stream(cur)
+        st["d2h"].wait_stream(cur)
+        for i, k0 in enumerate(range(0, K, chunk)):
+            b, c = i & 1, min(chunk, K - k0)
+            if i >= 2:
+                st["h2d"].wait_event(st["run"][b])           # kernel i-2 has consumed exc[b]
+            with torch.cuda.stream(st["h2d"]):
+                st["exc"][b][:c].copy_(exc_host[k0:k0 + c], non_blocking=True)
+                st["up"][b].record(st["h2d"])
+            cur.wait_event(st["up"][b])
+            if i >= 2:
+                cur.wait_event(st["down"][b])                # copy-out i-2 has drained tot[b]
+            self.step_many(st["exc"][b][:c], step_size, out=st["tot"][b][:c])
+            st["run"][b].record(cur)
+            st["d2h"].wait_event(st["run"][b])
+            with torch.cuda.stream(st["d2h"]):
+                out_host[k0:k0 + c].copy_(st["tot"][b][:c], non_blocking=True)
+                st["down"][b].record(st["d2h"])
+        cur.wait_stream(st["d2h"])
+        return out_host
+
     # ---- observers --------------------------------------------------------------------
     @property
     def current_forces(self) -> torch.Tensor:

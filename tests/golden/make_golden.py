@@ -232,6 +232,26 @@ def arm(pm):
                 cpf=cpf, forces=forces, dt=0.02)
 
 
+def readme_exact(pm):
+    """The README loop with the literal Python float 0.6 (not float32-rounded) and the
+    minimal-physio example with 40.0: the values SURVEY.md Appendix D quotes."""
+    m = pm.StandardMuscle()
+    tot = np.array([m.step(0.6, 1 / 50.0) for _ in range(10000)])
+    out = dict(standard_totals=tot, standard_fatigue=np.array(m.get_peripheral_fatigue()),
+               standard_cpf=m._fibers._current_peak_forces.copy(), standard_forces=m.current_forces.copy())
+    m = pm.PotvinFuglevandMuscle(120)
+    tot = np.array([m.step(40.0, 0.02) for _ in range(10000)])
+    out.update(potvin_totals=tot, potvin_cpf=m._fibers._current_peak_forces.copy(),
+               potvin_dur=m._pool._recruitment_durations.copy())
+    m = pm.StandardMuscle(32.0)
+    for _ in range(100):
+        m.step(0.0, 1.0)
+    for _ in range(100):
+        o = m.step(0.5, 1.0)
+    out.update(rest_then_half_output=np.array(o), rest_then_half_fatigue=np.array(m.get_peripheral_fatigue()))
+    return out
+
+
 def tables(pm):
     out = {}
     for n in (2, 33, 120, 340, 2000):
@@ -276,6 +296,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "halves.npz"), **halves(pm))
     np.savez_compressed(os.path.join(HERE, "arm.npz"), **arm(pm))
     np.savez_compressed(os.path.join(HERE, "tables.npz"), **tables(pm))
+    np.savez_compressed(os.path.join(HERE, "readme_exact.npz"), **readme_exact(pm))
     print("numpy", np.__version__)
     return 0
 

@@ -163,19 +163,35 @@ def test_readme_loop_config1():
     """BASELINE config #1: StandardMuscle(), 0.6 excitation, 50 fps, 10,000 steps;
     history of current_forces kept in a list as the README does (README.md:122-130)."""
     from pymuscle_b200 import StandardMuscle
-    g = golden("traj_standard_const06")
+    g = golden("readme_exact")
     muscle = StandardMuscle()
     outputs, history = [], []
     for _ in range(10000):
         outputs.append(muscle.step(0.6, 1 / 50.0))
         if len(outputs) in (1, 100, 10000):
             history.append(muscle.current_forces)
-    np.testing.assert_allclose(outputs, g["totals"][:, 0], rtol=1e-9, atol=1e-12)
-    cps = list(g["checkpoints"])
-    for h, step in zip(history, (0, 99, 9999)):
-        np.testing.assert_allclose(h, g["forces"][cps.index(step), 0], rtol=1e-9, atol=1e-10)
-    assert history[0] is not history[1]
+    np.testing.assert_allclose(outputs, g["standard_totals"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(history[-1], g["standard_forces"], rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(muscle._fibers.current_peak_forces, g["standard_cpf"], rtol=1e-9, atol=1e-10)
+    assert history[0] is not history[1] and not np.array_equal(history[0], history[1])
+    assert muscle.get_peripheral_fatigue() == pytest.approx(float(g["standard_fatigue"]), rel=1e-9)
+    # SURVEY.md Appendix D quotes these for the same run
+    assert outputs[0] == pytest.approx(0.5059615150545111, rel=1e-9)
+    assert outputs[9999] == pytest.approx(0.1435819929896607, rel=1e-9)
     assert muscle.get_peripheral_fatigue() == pytest.approx(0.5413389785180036, rel=1e-9)
+
+
+def test_physio_example_loop():
+    """examples/minimal-physio-example.py: PotvinFuglevandMuscle(120), 40.0, 10,000 steps."""
+    from pymuscle_b200 import PotvinFuglevandMuscle
+    g = golden("readme_exact")
+    muscle = PotvinFuglevandMuscle(120)
+    outputs = [muscle.step(40.0, 0.02) for _ in range(10000)]
+    np.testing.assert_allclose(outputs, g["potvin_totals"], rtol=1e-9)
+    np.testing.assert_allclose(muscle._fibers.current_peak_forces, g["potvin_cpf"], rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(muscle._pool._recruitment_durations, g["potvin_dur"], rtol=1e-12)
+    assert outputs[0] == pytest.approx(1311.8689626905448, rel=1e-9)
+    assert outputs[9999] == pytest.approx(403.39412010089995, rel=1e-9)
 
 
 def test_generic_composition_with_a_user_model():

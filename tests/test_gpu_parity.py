@@ -223,7 +223,7 @@ def test_arm_ragged_rows(cuda_device, precision):
     fat = b.get_peripheral_fatigue()
     want = np.array([1 - sum(g["cpf"][o:o + s.n]) / s.output_divisor
                      for o, s in zip(np.cumsum([0] + [s.n for s in specs[:-1]]), specs)])
-    np.testing.assert_allclose(fat[0].cpu().numpy(), want, rtol=1e-6, atol=1e-9)
+    close(fat[0].cpu().numpy(), want, precision, 1.0, "arm peripheral fatigue")
 
 
 def test_full_size_properties_config2(cuda_device):

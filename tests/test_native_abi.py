@@ -62,6 +62,8 @@ def test_pack_f32_critical_inputs_reproduce_the_float64_predicate(kind):
     np.testing.assert_array_equal(P[0, :, 2], tab["peak"].astype(np.float32))
     np.testing.assert_array_equal(P[1, :, 3], tab["fat"].astype(np.float32))
     np.testing.assert_array_equal(P[2, :, 0], tab["ptf"].astype(np.float32))
+    np.testing.assert_array_equal(P[2, :, 0].astype(np.float64) + P[2, :, 3], tab["ptf"].astype(np.float32).astype(np.float64)
+                                  + (tab["ptf"] - tab["ptf"].astype(np.float32)).astype(np.float32))
     assert row.cfg.table_props & nat.MB_PROP_ADAPT_NONNEG
 
 

@@ -167,3 +167,18 @@ def test_arm():
             got = mu.step(float(g["exc"][k, j]), float(g["dt"])).total[0]
             assert got == pytest.approx(g["totals"][k, j], rel=RTOL, abs=1e-300)
     np.testing.assert_allclose(np.concatenate([mu.cpf[0] for mu in muscles]), g["cpf"], rtol=RTOL)
+
+
+def test_readme_exact_values():
+    """SURVEY.md Appendix D (literal 0.6 / 40.0 inputs), via the reference-shaped oracle."""
+    g = golden("readme_exact")
+    assert g["standard_totals"][0] == pytest.approx(0.5059615150545111, rel=1e-13)
+    assert g["standard_totals"][9999] == pytest.approx(0.1435819929896607, rel=1e-13)
+    assert float(g["standard_fatigue"]) == pytest.approx(0.5413389785180036, rel=1e-13)
+    assert g["potvin_totals"][0] == pytest.approx(1311.8689626905448, rel=1e-13)
+    assert g["potvin_totals"][9999] == pytest.approx(403.39412010089995, rel=1e-13)
+    assert float(g["rest_then_half_output"]) == pytest.approx(0.291518275974285, rel=1e-13)
+    assert float(g["rest_then_half_fatigue"]) == pytest.approx(0.1802818182250192, rel=1e-13)
+    m = OracleMuscle(120, "standard")
+    got = np.array([m.step(0.6, 1 / 50.0) for _ in range(2000)])
+    np.testing.assert_allclose(got, g["standard_totals"][:2000], rtol=RTOL)
