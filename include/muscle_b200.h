@@ -140,7 +140,7 @@ int mb_step(const MbConfig* cfg, const void* params_dev,
  *   forces_every     f > 0: per-unit forces (and masks) of steps f-1, 2f-1, ... are written to
  *                    forces_dec_dev[(k / f), m, u] / mask_dec_dev; 0 = never
  *   forces_last_dev  [M, n] forces of the window's last step (current_forces); may be NULL
- * Returns MB_EUNSUPPORTED when n is outside the fused kernel's range (2..512); the
+ * Returns MB_EUNSUPPORTED when n is outside the fused kernel's range (2..480); the
  * caller then issues K mb_step launches instead (still on the GPU).
  */
 int mb_step_fused(const MbConfig* cfg, const void* params_dev,

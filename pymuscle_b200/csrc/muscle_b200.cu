@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(1024) k_peak_probe(int iters, double* sink) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) s += v[i];
         sink[t] = s;
-    } else {
+    } else if (KIND == 2) {
         float v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = 0.1f * (float)(i + 1) + 1e-3f * (float)(t & 15);
@@ -373,17 +373,85 @@ __global__ void __launch_bounds__(1024) k_peak_probe(int iters, double* sink) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) s += v[i];
         sink[t] = (double)s;
+    } else if (KIND == 3) {
+        // packed FP32x2 FMA (sm_100 fma.rn.f32x2 -> SASS FFMA2): 8 chains of 2 floats
+        unsigned long long v[8], b, c;
+        {
+            const float bf = 1.0f - 1e-7f * (float)(t & 7), cf = 1e-9f * (float)(t & 3);
+            asm("mov.b64 %0, {%1, %1};" : "=l"(b) : "f"(bf));
+            asm("mov.b64 %0, {%1, %1};" : "=l"(c) : "f"(cf));
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float x = 1.0f + 0.01f * (float)i;
+            asm("mov.b64 %0, {%1, %1};" : "=l"(v[i]) : "f"(x));
+        }
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(v[i]) : "l"(b), "l"(c));
+        }
+        float s = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float lo, hi;
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v[i]));
+            s += lo + hi;
+        }
+        sink[t] = (double)s;
+    } else if (KIND == 4) {
+        // ALU pipe: FMNMX chains
+        float v[8];
+        const float lo = 0.25f + 1e-3f * (float)(t & 7), hi = 0.75f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.1f * (float)(i + 1);
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = fminf(v[i] + 0.0f * 0.0f, hi);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], lo);
+            }
+        }
+        float s = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += v[i];
+        sink[t] = (double)s;
+    } else {
+        // issue mix of the fused kernel: per 8 "instructions" 5 FFMA, 2 FMNMX, 1 MUFU
+        float v[8];
+        const float b = 1.0f - 1e-7f * (float)(t & 7), c = 1e-3f * (float)(t & 3), hi = 0.75f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.1f * (float)(i + 1);
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float x = v[i];
+                x = fmaf(x, b, c); x = fmaf(x, b, c); x = fminf(x, hi); x = fmaf(x, b, c);
+                x = ex2_approx(-x); x = fmaf(x, b, c); x = fmaxf(x, c); x = fmaf(x, b, c);
+                v[i] = x;
+            }
+        }
+        float s = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += v[i];
+        sink[t] = (double)s;
     }
 }
 
 extern "C" int mb_peak_probe(int32_t kind, int32_t blocks, int32_t threads, int32_t iters, void* sink_dev,
                              int64_t* lane_ops, void* stream) {
-    if (kind < 0 || kind > 2 || blocks <= 0 || threads <= 0 || threads > 1024 || iters <= 0 || !sink_dev)
+    if (kind < 0 || kind > 5 || blocks <= 0 || threads <= 0 || threads > 1024 || iters <= 0 || !sink_dev)
         return fail(MB_EINVAL, "mb_peak_probe: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     if (kind == 0) k_peak_probe<0><<<blocks, threads, 0, st>>>(iters, (double*)sink_dev);
     else if (kind == 1) k_peak_probe<1><<<blocks, threads, 0, st>>>(iters, (double*)sink_dev);
-    else k_peak_probe<2><<<blocks, threads, 0, st>>>(iters, (double*)sink_dev);
+    else if (kind == 2) k_peak_probe<2><<<blocks, threads, 0, st>>>(iters, (double*)sink_dev);
+    else if (kind == 3) k_peak_probe<3><<<blocks, threads, 0, st>>>(iters, (double*)sink_dev);
+    else if (kind == 4) k_peak_probe<4><<<blocks, threads, 0, st>>>(iters, (double*)sink_dev);
+    else k_peak_probe<5><<<blocks, threads, 0, st>>>(iters, (double*)sink_dev);
     MB_CUDA_OK(cudaGetLastError());
     if (lane_ops) *lane_ops = (int64_t)blocks * threads * 64 * (int64_t)iters;
     return MB_OK;
@@ -474,7 +542,7 @@ extern "C" int mb_peripheral_fatigue(const MbConfig* cfg, int64_t rows, int64_t 
 
 // ---- fused geometry ---------------------------------------------------------------------
 struct FusedGeom {
-    int U, q, G, Gp, T, P, threads, smem;
+    int U, q, G, Gp, T, P, pitch, ncomp, threads, smem;
     int64_t blocks;
 };
 
@@ -483,13 +551,15 @@ static int env_int(const char* name, int dflt) {
     return (v && *v) ? atoi(v) : dflt;
 }
 
+static const int kFusedMaxUnits = 480;     // compute threads per block <= 480, + 1 service warp = 512
+
 static int fused_geometry(const MbConfig& c, int64_t M, int32_t n, int32_t K, int32_t upt, FusedGeom* g) {
-    if (n < 2 || n > 512) return fail(MB_EUNSUPPORTED, "fused kernel supports 2 <= n <= 512 units per muscle (got %d)", n);
+    if (n < 2 || n > kFusedMaxUnits)
+        return fail(MB_EUNSUPPORTED, "fused kernel supports 2 <= n <= %d units per muscle (got %d)", kFusedMaxUnits, n);
     if (M <= 0 || K <= 0) return fail(MB_EINVAL, "M and K must be positive");
     const bool f32 = c.precision == MB_F32;
     const int esz = f32 ? 4 : 8;
-    int q = 512 / n;
-    if (q < 1) q = 1;
+    int q = kFusedMaxUnits / n;
     if (upt != 0 && upt != 1 && upt != 2 && upt != 4) return fail(MB_EINVAL, "units_per_thread must be 0, 1, 2 or 4");
     if (!f32 && upt == 4) return fail(MB_EINVAL, "units_per_thread 4 is FP32-only");
     int U = upt;
@@ -503,25 +573,34 @@ static int fused_geometry(const MbConfig& c, int64_t M, int32_t n, int32_t K, in
     g->U = U; g->q = q; g->G = q * U;
     const int vl = 16 / esz;
     g->Gp = (g->G + vl - 1) / vl * vl;
-    g->threads = (q * n + 31) / 32 * 32;
-    const int step_bytes = q * n * U * esz;                 // one step of the force tile
+    g->ncomp = (q * n + 31) / 32 * 32;
+    g->threads = g->ncomp + 32;                              // + the service warp
+    const int vec_bytes = U * esz;
     int T = env_int("MB_FUSED_T", 0);                        // tuning override (steps per tile)
     if (T <= 0) {
-        T = (60 * 1024) / step_bytes;
-        if (T > 16) T = 16;
+        T = (64 * 1024) / (2 * q * (n + 8) * vec_bytes);     // both force-tile buffers within ~64 KB
+        if (T > 8) T = 8;
     }
     if (T < 1) T = 1;
     if (T > K) T = K;
     g->T = T;
-    // lanes per (step, q) row of the reduction: as many as fill the block once
+    // lanes per (step, q) row in the service warp: fill the warp once if possible
     int P = env_int("MB_FUSED_P", 0);
     if (P != 1 && P != 2 && P != 4 && P != 8 && P != 16 && P != 32) {
         P = 32;
-        while (P > 1 && (T * q * P > g->threads || P > n)) P >>= 1;
+        while (P > 1 && (T * q * P > 32 || P > n)) P >>= 1;
     }
     g->P = P;
-    g->smem = 16 + 2 * T * g->Gp * esz + T * step_bytes;
-    if (g->smem > 200 * 1024) return fail(MB_EUNSUPPORTED, "fused kernel: tile does not fit in shared memory");
+    // row pitch in vectors: for 16-byte vectors make pitch == P (mod 8) so that the 8 lanes of a
+    // quarter-warp (8/P rows x P parts, or 8 rows when P == 1) hit 8 different 16-byte bank groups
+    int pitch = n;
+    if (vec_bytes == 16 && P <= 8) {
+        const int want = P % 8;
+        while (pitch % 8 != want) ++pitch;
+    }
+    g->pitch = pitch;
+    g->smem = 64 + 4 * T * g->Gp * esz + 2 * T * q * pitch * vec_bytes;
+    if (g->smem > 110 * 1024) return fail(MB_EUNSUPPORTED, "fused kernel: tile does not fit in shared memory");
     g->blocks = (M + g->G - 1) / g->G;
     return MB_OK;
 }
@@ -579,6 +658,7 @@ extern "C" int mb_step_fused(const MbConfig* cfg, const void* params_dev, int64_
     K2Args a;
     memset(&a, 0, sizeof(a));
     a.params = params_dev; a.M = M; a.n = n; a.q = g.q; a.K = K; a.T = g.T; a.P = g.P; a.G = g.G; a.Gp = g.Gp;
+    a.pitch = g.pitch; a.ncomp = g.ncomp;
     a.exc = exc_dev; a.exc_stride_k = exc_stride_k;
     if (exc_stride_k == 0) {
         a.exc_mode = 2;
