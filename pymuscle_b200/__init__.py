@@ -14,3 +14,4 @@ from .models import PotvinFuglevand2017MotorNeuronPool  # noqa: F401
 from .models import PyMuscleFibers  # noqa: F401
 from .engine import MuscleBatch  # noqa: F401
 from .tables import MuscleSpec, PoolParams, FibersParams  # noqa: F401
+from .distributed import ShardedMuscleBatch, shard_bounds  # noqa: F401

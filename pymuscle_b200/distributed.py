@@ -1,0 +1,179 @@
+"""
+Muscle batches sharded over the GPUs of one box (one process per GPU).
+
+Muscles never read each other's state (the reference keeps one pool and one
+fibers object per Muscle, pymuscle/muscle.py:50-51, and callers loop over
+separate instances, examples/envs/muscled_hopper.py:33-34), so the batch axis
+is cut into contiguous blocks of rows, one per rank, and every rank advances
+its own rows with the same kernels as a single-GPU MuscleBatch.  There is NO
+collective on the data path.  The only exchange is the optional gather of
+per-muscle totals (``gather=True`` / ``gather_totals``): one all-gather over
+``torch.distributed`` (NCCL over NVLink on the GPUs, gloo in the CPU tests),
+issued per step or per fused window, optionally asynchronously so that it
+overlaps the next window.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Tuple, Union
+
+import torch
+import torch.distributed as dist
+
+from .tables import MuscleSpec
+
+
+def shard_bounds(total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Rows [lo, hi) owned by ``rank``: contiguous blocks, the first ``total % world``
+    ranks hold one row more."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError(f"bad rank {rank} of world {world}")
+    if total < 0:
+        raise ValueError("total must be non-negative")
+    base, extra = divmod(int(total), int(world))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_sizes(total: int, world: int):
+    return [shard_bounds(total, r, world)[1] - shard_bounds(total, r, world)[0] for r in range(world)]
+
+
+class _Handle:
+    """An all-gather in flight: ``wait()`` returns the gathered tensor."""
+
+    def __init__(self, work, pieces, widths, tail):
+        self._work, self._pieces, self._widths, self._tail = work, pieces, widths, tail
+
+    def wait(self) -> torch.Tensor:
+        if self._work is not None:
+            self._work.wait()
+            self._work = None
+        t = torch.cat([p[..., :w] for p, w in zip(self._pieces, self._widths)], dim=-1) \
+            if len(self._pieces) > 1 else self._pieces[0]
+        return t.reshape(*t.shape[:-1], *self._tail) if self._tail else t
+
+    def result(self, async_op: bool):
+        return self if async_op else self.wait()
+
+
+class ShardedMuscleBatch:
+    """``total_rows`` rows of ``spec`` spread over the ranks of ``group``.
+
+    Every rank constructs this with the same arguments.  ``step`` / ``step_many`` accept
+    either this rank's slice of the excitations or the global tensor (which is then
+    sliced); they return this rank's totals, or the totals of all rows when
+    ``gather=True``.
+
+    engine_cls   the per-rank engine (default: MuscleBatch, CUDA only).  The CPU tests
+                 inject an oracle-backed engine to exercise the sharding logic over gloo.
+    """
+
+    def __init__(self, spec: Union[MuscleSpec, Sequence[MuscleSpec]], total_rows: int,
+                 device=None, precision="f32", group: Optional[dist.ProcessGroup] = None,
+                 engine_cls=None, **engine_kwargs):
+        self.group = group
+        if dist.is_available() and dist.is_initialized():
+            self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        else:
+            self.rank, self.world = 0, 1
+        self.total_rows = int(total_rows)
+        if self.total_rows < self.world:
+            raise ValueError(f"{self.total_rows} rows cannot be spread over {self.world} ranks")
+        self.row_lo, self.row_hi = shard_bounds(self.total_rows, self.rank, self.world)
+        self.sizes = shard_sizes(self.total_rows, self.world)
+        if engine_cls is None:
+            from .engine import MuscleBatch
+            engine_cls = MuscleBatch
+        self.local = engine_cls(spec, self.row_hi - self.row_lo, device, precision, **engine_kwargs)
+        self.S = self.local.S
+
+    # ---- shapes -----------------------------------------------------------------------
+    @property
+    def local_rows(self) -> int:
+        return self.row_hi - self.row_lo
+
+    @property
+    def n_muscles_local(self) -> int:
+        return self.local_rows * self.S
+
+    @property
+    def n_muscles_total(self) -> int:
+        return self.total_rows * self.S
+
+    def _local_slice(self, x, per_step: bool, global_input: Optional[bool]):
+        """This rank's part of an excitation argument.  The muscle axis (axis 1 of a
+        [K, ...] window, else axis 0) may hold this rank's rows or all rows, as [rows],
+        [rows * S] or [rows * L]; ``global_input`` forces the interpretation, None guesses
+        (a size that fits the local shard is taken as local)."""
+        ax = 1 if per_step else 0
+        if self.world == 1 or not isinstance(x, torch.Tensor) or x.dim() <= ax or global_input is False:
+            return x
+        size, S, L = int(x.shape[ax]), self.S, self.local.L
+        flat = x.dim() == ax + 1
+        if global_input is None and (size == self.local_rows or (flat and size in (self.local_rows * S, self.local_rows * L))):
+            return x
+        for per_row in ((1, S, L) if flat else (1,)):
+            if size == self.total_rows * per_row:
+                return x.narrow(ax, self.row_lo * per_row, self.local_rows * per_row)
+        if global_input:
+            raise AssertionError(f"excitation of shape {tuple(x.shape)} does not cover {self.total_rows} rows")
+        return x
+
+    # ---- stepping ---------------------------------------------------------------------
+    def step(self, excitation, step_size: float, gather: bool = False,
+             global_input: Optional[bool] = None, **kw):
+        out = self.local.step(self._local_slice(excitation, False, global_input), step_size, **kw)
+        return self.gather_totals(out) if gather else out
+
+    def step_many(self, excitations, step_size: float, gather: bool = False,
+                  global_input: Optional[bool] = None, **kw):
+        per_step = kw.get("steps") is None                   # [M] + steps=K is the constant form
+        out = self.local.step_many(self._local_slice(excitations, per_step, global_input), step_size, **kw)
+        if gather:
+            tot = out[0] if isinstance(out, tuple) else out
+            g = self.gather_totals(tot)
+            return (g,) + tuple(out[1:]) if isinstance(out, tuple) else g
+        return out
+
+    # ---- the one exchange: all ranks' per-muscle totals ---------------------------------
+    def gather_totals(self, local: torch.Tensor, async_op: bool = False):
+        """All-gather along the muscle axis.  ``local`` is [..., local_rows * S] (what ``step`` of
+        a uniform batch and ``step_many`` return) or [..., local_rows, S] (``step`` of a ragged
+        batch); the result has the same form with ``total_rows`` in place of ``local_rows``, on
+        every rank (a handle with ``wait()`` when ``async_op``).  Shards of unequal size are
+        padded to the largest one for the wire."""
+        S = self.S
+        two_d = S > 1 and local.dim() >= 2 and tuple(local.shape[-2:]) == (self.local_rows, S)
+        flat = local.reshape(*local.shape[:-2], -1) if two_d else local
+        if flat.shape[-1] != self.local_rows * S:
+            raise AssertionError(
+                f"expected {self.local_rows * S} local totals on the last axis, got {tuple(local.shape)}")
+        tail = (self.total_rows, S) if two_d else None
+        if self.world == 1:
+            return _Handle(None, [flat], [flat.shape[-1]], tail).result(async_op)
+        widths = [s * S for s in self.sizes]
+        send = flat.contiguous()
+        if send.shape[-1] != max(widths):
+            pad = send.new_zeros(*send.shape[:-1], max(widths))
+            pad[..., : send.shape[-1]] = send
+            send = pad
+        pieces = [torch.empty_like(send) for _ in range(self.world)]
+        work = dist.all_gather(pieces, send, group=self.group, async_op=True)
+        return _Handle(work, pieces, widths, tail).result(async_op)
+
+    # ---- observers / state ----------------------------------------------------------------
+    def get_peripheral_fatigue(self, gather: bool = False):
+        out = self.local.get_peripheral_fatigue()
+        return self.gather_totals(out) if gather else out
+
+    def state_dict(self) -> dict:
+        """This rank's shard of the state plus where it sits in the global batch."""
+        sd = dict(self.local.state_dict())
+        sd["row_range"] = (self.row_lo, self.row_hi)
+        sd["total_rows"] = self.total_rows
+        return sd
+
+    def load_state_dict(self, state: dict):
+        if tuple(state.get("row_range", (self.row_lo, self.row_hi))) != (self.row_lo, self.row_hi):
+            raise ValueError("state_dict belongs to a different shard")
+        self.local.load_state_dict({k: v for k, v in state.items() if k not in ("row_range", "total_rows")})
