@@ -1,25 +1,30 @@
 // mb_fused.cuh -- K2: K fused steps per launch, unit state in registers.
 //
 // Uniform batch: M muscles x n units.  A block owns G = q*U consecutive muscles.
+// Muscle group tq (U muscles) occupies `ns` consecutive threads, ns = n rounded up to a
+// multiple of 8; thread tq*ns + u handles unit u of muscles tq*U .. +U-1: its U
+// unit-instances share one set of per-unit parameters (registers, loaded once per window
+// as 128-bit vectors) and give U independent dependency chains.  Per step: one vector LDS
+// (U excitations), the arithmetic of mb_core.cuh, one vector STS (U forces).
 //
-//   compute warps   thread t < q*n handles unit (t % n) of muscles (t / n)*U .. +U-1:
-//                   its U unit-instances share one set of per-unit parameters (registers,
-//                   loaded once per window as 128-bit vectors) and give U independent
-//                   dependency chains.  Per step: one vector LDS (U excitations), the
-//                   arithmetic of mb_core.cuh, one vector STS (U forces).
-//   service warp    one extra warp per block.  It (a) stages the per-step excitations
-//                   two tiles ahead with cp.async.bulk (1-D bulk copy per step row,
-//                   mbarrier complete_tx) and (b) turns the force tile of the previous
-//                   T steps into per-step, per-muscle totals while the compute warps are
-//                   already producing the next tile.
+// Per-(step, muscle) totals without any block-wide barrier.  Time is cut into tiles of
+// T = 8 steps and the sum over a muscle's units is done in two stages:
 //
-// Shared memory:
-//   exc ring    [4][T][Gp]           excitations, one slot per tile of T steps
-//   force tile  [2][T][q][pitch][U]  unit forces, double-buffered; pitch >= n is chosen so
-//                                    that the service warp's row-parallel 128-bit loads are
-//                                    bank-conflict free
-// Synchronisation is mbarrier-only inside the loop (exc_full[4], ft_full[2], ft_free[2]):
-// compute warps never wait for each other, only for data.
+//   stage 1  warp-local.  During a tile every warp writes its lanes' forces into its own
+//            tile FTw[T][32] (row pitch 33 vectors).  After the tile (one __syncwarp) lane
+//            (part = lane >> 3, s = lane & 7) sums the 8 columns part*8 .. +7 of row s with
+//            8 independent 128-bit LDS (bank-conflict free) and stores the partial into
+//            PT[tile & 3][s][4*warp + part].  Group boundaries are multiples of 8 threads, so
+//            every 8-column part belongs to exactly one muscle group.
+//   stage 2  one warp per tile (rotating: warp (tile % warps)) waits on the mbarrier that
+//            counts the warps' stage-1 arrivals, sums the ns/8 partials of every
+//            (step, muscle) and stores the totals to HBM (coalesced).
+//
+// PT is a ring of 4 tiles guarded by mbarriers (pfull: 1 arrival per warp; pfree: 1 arrival
+// by the stage-2 warp), so warps may drift up to 3 tiles apart and never wait for each
+// other in steady state.  Warp 0 additionally stages the per-step excitations two tiles
+// ahead with cp.async.bulk (1-D bulk copy per step row, mbarrier complete_tx) into an
+// 8-slot ring; consumers wait on the slot's mbarrier.
 //
 // HBM traffic per window: state in/out (32 B/unit) plus excitations and totals
 // (2*sizeof(T)/n B per unit-step) -- see DESIGN.md.
@@ -28,12 +33,15 @@
 
 namespace mb {
 
-constexpr int kExcSlots = 4;
+constexpr int kExcSlots = 8;     // excitation ring (tiles)
+constexpr int kPtSlots = 4;      // partial-sum ring (tiles)
+constexpr int kTile = 8;         // steps per tile (stage 1 maps lane & 7 to the step)
+constexpr int kFtPitch = 33;     // row pitch of a warp's force tile, in vectors (odd => conflict free)
 
 struct K2Args {
     const void* params;
     int64_t M;
-    int32_t n, q, K, T, P, G, Gp, pitch, ncomp;
+    int32_t n, ns, q, K, T, G, Gp, npg, ptp;   // ns: threads per muscle group; npg = ns/8 parts per group; ptp: PT row pitch
     const void* exc;
     int64_t exc_stride_k;
     int32_t exc_mode;            // 0 = bulk copy, 1 = element-wise loads, 2 = constant over the window
@@ -47,6 +55,7 @@ struct K2Args {
     void* forces_last;
     int32_t peripheral;
     double dt, adk_d, max_dur;
+    double decay_d;              // exp(-dt/tau): per-step factor of exp(-dur/tau) for a firing unit
     ScalF sf;
     ScalD sd;
 };
@@ -102,7 +111,10 @@ template <typename T, int U> struct alignas(sizeof(T) * U) VecU { T v[U]; };
 // CENTRAL: 0 = pool.apply_fatigue off (adaptation is the identity)
 //          1 = on, fast path: the launcher has checked that (a) the adaptation of a
 //              recruited unit cannot be negative and (b) max_duration/tau is so large
-//              that the duration clamp cannot change exp(-dur/tau); both clamps drop out
+//              that the duration clamp cannot change exp(-dur/tau); both clamps drop out.
+//              E = exp(-dur/tau) is carried by recurrence -- a firing step multiplies it by
+//              exp(-dt/tau) -- and re-synchronised with one ex2 per tile from the exact
+//              counter, which replaces the per-step MUFU of the adaptation curve
 //          2 = on, general path with both clamps (pool:202-206, :221)
 template <int FIB, int CENTRAL, int U>
 struct CoreF32 {
@@ -111,8 +123,8 @@ struct CoreF32 {
     using ParamVec = float4;
     UnitF p;
     ScalF sc;
-    float fatdt, rdidt, dtk;
-    float hi[U], lo[U], cpf[U], cnt[U], arg0[U], room[U];
+    float fatdt, rdidt, dtk, decay;
+    float hi[U], lo[U], cpf[U], cnt[U], arg0[U], room[U], E[U];
 
     __device__ __forceinline__ void load(const K2Args& a, int u) {
         p = load_unit((const float4*)a.params, a.n, u);
@@ -120,6 +132,7 @@ struct CoreF32 {
         fatdt = a.peripheral ? (float)((double)p.fat * a.dt) : 0.0f;
         rdidt = a.peripheral ? (float)((double)p.rdi * a.dt) : 0.0f;
         dtk = (float)(a.dt * a.adk_d);
+        decay = (float)a.decay_d;
     }
     __device__ __forceinline__ double rest_capacity() const { return (double)p.ptf + (double)p.ptf_lo; }
     __device__ __forceinline__ void init(int j, const K2Args& a, double c, double d0) {
@@ -129,6 +142,13 @@ struct CoreF32 {
         room[j] = (p.ptf - hi[j]) + p.ptf_lo;            // peak - hi: the upper bound of lo (pmf:104-105)
         cnt[j] = 0.0f;
         arg0[j] = (float)(d0 * a.adk_d);
+        E[j] = 1.0f;
+    }
+    __device__ __forceinline__ void begin_tile() {
+        if (CENTRAL == 1) {
+#pragma unroll
+            for (int j = 0; j < U; ++j) E[j] = ex2_approx(fmaf(cnt[j], dtk, arg0[j]));
+        }
     }
     // one step of instance j; returns the unit force
     __device__ __forceinline__ float step(int j, float e, bool& on) {
@@ -136,17 +156,20 @@ struct CoreF32 {
         float fr;
         if (CENTRAL == 0) {
             fr = on ? r : 0.0f;
+        } else if (CENTRAL == 1) {
+            const float q = fmaf(r, p.phir, -p.phir6);                     // pool:231-232
+            fr = r - fmaf(-q, E[j], q);                                    // pool:217-221, :121 (dur BEFORE the update)
+            fr = on ? fr : 0.0f;
+            if (on) {                                                      // pool:196-197
+                cnt[j] += 1.0f;
+                E[j] *= decay;
+            }
         } else {
             float arg = fmaf(cnt[j], dtk, arg0[j]);
-            if (on) cnt[j] += 1.0f;                                        // pool:196-197
-            if (CENTRAL == 1) {
-                fr = r - pool_adaptation(p, r, arg);
-                fr = on ? fr : 0.0f;
-            } else {
-                arg = fmaxf(arg, sc.argmin);
-                const float r0 = on ? r : 0.0f;
-                fr = r0 - fmaxf(pool_adaptation(p, r0, arg), 0.0f);
-            }
+            if (on) cnt[j] += 1.0f;
+            arg = fmaxf(arg, sc.argmin);
+            const float r0 = on ? r : 0.0f;
+            fr = r0 - fmaxf(pool_adaptation(p, r0, arg), 0.0f);
         }
         float nf;
         const float F = fibers_force(p, sc, fr, cpf[j], nf);
@@ -193,6 +216,10 @@ struct CoreF32 {
 };
 
 // ---- FP64 mode ------------------------------------------------------------------------
+// Durations are accumulated exactly as the reference does (dur += dt, clamped).  The
+// adaptation factor E = exp(-dur/tau) is carried by recurrence (a firing step multiplies it
+// by exp(-dt/tau); a clamped duration pins it to exp(-max_duration/tau)) and recomputed
+// with a full-precision exp at every tile start, so its error stays at a few ulps.
 template <int FIB, int CENTRAL, int U>
 struct CoreF64 {
     using T = double;
@@ -200,8 +227,8 @@ struct CoreF64 {
     using ParamVec = double2;
     UnitD p;
     ScalD sc;
-    double fatdt, rdidt, dt, max_dur;
-    double cpf[U], dur[U];
+    double fatdt, rdidt, dt, max_dur, decay, Emax;
+    double cpf[U], dur[U], E[U];
 
     __device__ __forceinline__ void load(const K2Args& a, int u) {
         p = load_unit((const double2*)a.params, a.n, u);
@@ -210,18 +237,34 @@ struct CoreF64 {
         rdidt = a.peripheral ? p.rdi * a.dt : 0.0;
         dt = a.dt;
         max_dur = a.max_dur;
+        decay = a.decay_d;
+        Emax = CENTRAL ? exp(a.max_dur * a.sd.mitau) : 0.0;
     }
     __device__ __forceinline__ double rest_capacity() const { return p.ptf; }
     __device__ __forceinline__ void init(int j, const K2Args&, double c, double d0) {
         cpf[j] = c;
         dur[j] = d0;
+        E[j] = 1.0;
+    }
+    __device__ __forceinline__ void begin_tile() {
+        if (CENTRAL) {
+#pragma unroll
+            for (int j = 0; j < U; ++j) E[j] = exp(dur[j] * sc.mitau);     // pool:217-218
+        }
     }
     __device__ __forceinline__ double step(int j, double e, bool& on) {
         const double r = pool_rate(p, sc, e, on);
         double fr = r;
         if (CENTRAL) {
-            fr = pool_adapt(p, sc, r, dur[j]);
-            dur[j] = duration_update(dur[j], r > 0.0, dt, max_dur);
+            const double q = fma(r, p.phir, -p.phir6);                     // pool:231-232
+            const double ad = q * (1.0 - E[j]);                            // pool:217-219 (dur BEFORE the update)
+            fr = r - ((ad < 0.0) ? 0.0 : ad);                              // pool:221, :121
+            if (r > 0.0) {                                                 // pool:196-197
+                const double dn = dur[j] + dt;
+                const bool clamp = dn > max_dur;                           // pool:202-203
+                dur[j] = clamp ? max_dur : dn;
+                E[j] = clamp ? Emax : E[j] * decay;
+            }
         }
         double nf;
         const double F = fibers_force(p, sc, fr, cpf[j], nf);
@@ -237,7 +280,7 @@ struct CoreF64 {
 };
 
 // ======================================================================================
-// service warp: excitation staging + per-(step, muscle) totals
+// excitation staging (warp 0): tile `tile` of the window -> ring slot tile & 7
 // ======================================================================================
 template <typename T>
 __device__ __forceinline__ void publish_exc(const K2Args& a, T* exc_s, uint64_t* exc_full, int tile, int64_t m0,
@@ -245,7 +288,7 @@ __device__ __forceinline__ void publish_exc(const K2Args& a, T* exc_s, uint64_t*
     const int k0 = tile * a.T;
     const int steps = min(a.T, a.K - k0);
     const int slot = tile & (kExcSlots - 1);
-    T* dst = exc_s + (size_t)slot * a.T * a.Gp;
+    T* dst = exc_s + slot * a.T * a.Gp;
     const T* src = (const T*)a.exc + (int64_t)k0 * a.exc_stride_k + m0;
     if (a.exc_mode == 0) {
         if (lane == 0) {
@@ -265,46 +308,6 @@ __device__ __forceinline__ void publish_exc(const K2Args& a, T* exc_s, uint64_t*
     }
 }
 
-// Rows = steps*q, each `n` vectors of U forces (U muscles side by side), row pitch
-// `pitch` vectors.  P lanes (a power of two) share a row, 32/P rows are summed per pass.
-template <typename Core, int U>
-__device__ __forceinline__ void tile_row_sums(const K2Args& a, const Core& core, const typename Core::T* ftb,
-                                              int steps, int k0, int64_t m0, int gcount, int lane) {
-    using T = typename Core::T;
-    using V = VecU<T, U>;
-    const int P = a.P, n = a.n;
-    const int rows = steps * a.q;
-    const int rows_per_pass = 32 / P;
-    const int part = lane & (P - 1);
-    T* totals = (T*)a.totals;
-    for (int r0 = 0; r0 < rows; r0 += rows_per_pass) {
-        const int row = r0 + lane / P;
-        const bool active = row < rows;
-        const V* rp = (const V*)ftb + (size_t)(active ? row : 0) * a.pitch;
-        T acc[U];
-#pragma unroll
-        for (int j = 0; j < U; ++j) acc[j] = 0;
-#pragma unroll 4
-        for (int c = part; c < n; c += P) {
-            const V v = rp[c];
-#pragma unroll
-            for (int j = 0; j < U; ++j) acc[j] += v.v[j];
-        }
-        for (int o = P >> 1; o > 0; o >>= 1) {
-#pragma unroll
-            for (int j = 0; j < U; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
-        }
-        if (active && part == 0 && totals) {
-            const int s = row / a.q, tq = row - s * a.q;
-#pragma unroll
-            for (int j = 0; j < U; ++j) {
-                const int g = tq * U + j;
-                if (g < gcount) totals[(int64_t)(k0 + s) * a.totals_stride_k + m0 + g] = core.out_scale(acc[j]);
-            }
-        }
-    }
-}
-
 // ======================================================================================
 // the kernel
 // ======================================================================================
@@ -313,30 +316,34 @@ __device__ __forceinline__ void k2_body(const K2Args& a) {
     using T = typename Core::T;
     using V = VecU<T, U>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t* exc_full = (uint64_t*)smem_raw;            // [4]
-    uint64_t* ft_full = exc_full + kExcSlots;            // [2]
-    uint64_t* ft_free = ft_full + 2;                     // [2]
-    T* exc_s = (T*)(smem_raw + 64);                      // [4][T][Gp]
-    T* ft = exc_s + kExcSlots * a.T * a.Gp;              // [2][T][q][pitch][U]
+    uint64_t* exc_full = (uint64_t*)smem_raw;            // [8]
+    uint64_t* pfull = exc_full + kExcSlots;              // [4]  stage-1 partials of a tile complete
+    uint64_t* pfree = pfull + kPtSlots;                  // [4]  stage 2 has consumed them
+    T* exc_s = (T*)(smem_raw + 128);                     // [8][T][Gp]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    V* ft = (V*)(exc_s + kExcSlots * a.T * a.Gp);        // [nwarps][kTile][kFtPitch]
+    V* pt = ft + nwarps * kTile * kFtPitch;              // [4][kTile][ptp]
+    const int pt_tile = kTile * a.ptp;
 
-    const int tid = threadIdx.x, lane = tid & 31;
     const int n = a.n;
-    const bool is_service = tid >= a.ncomp;
     const int64_t m0 = (int64_t)blockIdx.x * a.G;
     const int gcount = (int)min((int64_t)a.G, a.M - m0);
     const int ntiles = (a.K + a.T - 1) / a.T;
-    const int tile_vecs = a.T * a.q * a.pitch;           // vectors per force-tile buffer
 
     if (tid == 0) {
         for (int i = 0; i < kExcSlots; ++i) mbar_init(&exc_full[i], 1);
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&ft_full[i], a.ncomp / 32);         // one arrival per compute warp
-            mbar_init(&ft_free[i], 1);                    // one arrival by the service warp
+        for (int i = 0; i < kPtSlots; ++i) {
+            mbar_init(&pfull[i], nwarps);
+            mbar_init(&pfree[i], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // columns of muscles beyond the batch read as 0 excitation (never recruited)
+    // muscles beyond the batch read 0 excitation (never recruited); idle lanes contribute 0 force
     for (int i = tid; i < kExcSlots * a.T * a.Gp; i += blockDim.x) exc_s[i] = T(0);
+    {
+        T* z = (T*)ft;
+        for (int i = tid; i < nwarps * kTile * kFtPitch * U; i += blockDim.x) z[i] = T(0);
+    }
     __syncthreads();
     if (a.exc_mode == 2) {                                // constant excitation: fill slot 0 once
         const T* src = (const T*)a.exc + m0;
@@ -345,31 +352,15 @@ __device__ __forceinline__ void k2_body(const K2Args& a) {
             if (g < gcount) exc_s[i] = src[g];
         }
         __syncthreads();
+    } else if (warp == 0) {
+        for (int t = 0; t < min(2, ntiles); ++t) publish_exc<T>(a, exc_s, exc_full, t, m0, gcount, lane);
     }
 
+    const int tq = tid / a.ns;
+    const int u_raw = tid - tq * a.ns;
+    const bool has_unit = tq < a.q && u_raw < n;
+    const int u = has_unit ? u_raw : 0;
     Core core;
-    if (is_service) {
-        // ------------------------------ service warp ------------------------------------
-        core.load(a, 0);                                   // only the output scaling is used here
-        if (a.exc_mode != 2)
-            for (int t = 0; t < min(2, ntiles); ++t) publish_exc<T>(a, exc_s, exc_full, t, m0, gcount, lane);
-        for (int tile = 0; tile < ntiles; ++tile) {
-            if (a.exc_mode != 2 && tile + 2 < ntiles) publish_exc<T>(a, exc_s, exc_full, tile + 2, m0, gcount, lane);
-            const int b = tile & 1;
-            const int k0 = tile * a.T;
-            mbar_wait(&ft_full[b], (uint32_t)((tile >> 1) & 1));
-            tile_row_sums<Core, U>(a, core, (const T*)((const V*)ft + (size_t)b * tile_vecs), min(a.T, a.K - k0), k0,
-                                   m0, gcount, lane);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&ft_free[b]);
-        }
-        return;
-    }
-
-    // ---------------------------------- compute warps -----------------------------------
-    const bool has_unit = tid < a.q * n;
-    const int u = has_unit ? tid % n : 0;
-    const int tq = has_unit ? tid / n : 0;
     core.load(a, u);
 
     T F[U];
@@ -385,19 +376,48 @@ __device__ __forceinline__ void k2_body(const K2Args& a) {
         F[j] = 0;
     }
 
-    const int step_stride = a.q * a.pitch;               // vectors per step in the force tile
+    // stage 2: totals of tile `t` from the partials PT[t & 3]; executed by one whole warp
+    auto stage2 = [&](int t) {
+        const int pb = t & (kPtSlots - 1);
+        mbar_wait(&pfull[pb], (uint32_t)((t / kPtSlots) & 1));
+        if (a.totals) {
+            const int k0 = t * a.T;
+            const int steps = min(a.T, a.K - k0);
+            const T* pp = (const T*)(pt + pb * pt_tile);
+            T* totals = (T*)a.totals;
+            for (int idx = lane; idx < steps * a.G; idx += 32) {          // idx = s*G + g, g = tqo*U + j
+                const int s = idx / a.G, g = idx - s * a.G;
+                const int tqo = g / U, j = g - tqo * U;
+                const T* src = pp + (s * a.ptp + tqo * a.npg) * U + j;
+                T acc = src[0];
+                for (int q2 = 1; q2 < a.npg; ++q2) acc += src[q2 * U];
+                if (g < gcount) totals[(int64_t)(k0 + s) * a.totals_stride_k + m0 + g] = core.out_scale(acc);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&pfree[pb]);
+    };
+
+    V* ftw = ft + warp * (kTile * kFtPitch);              // this warp's force tile
+    V* const fwr = ftw + lane;                            // compute: row s at fwr + s*kFtPitch
+    const V* const frd = ftw + (lane & 7) * kFtPitch + (lane >> 3) * 8;   // stage 1: row lane&7, part lane>>3
+    const int pt_col = warp * 4 + (lane >> 3);
+    const bool part_used = pt_col < a.q * a.npg;
+
     for (int tile = 0; tile < ntiles; ++tile) {
         const int k0 = tile * a.T;
         const int steps = min(a.T, a.K - k0);
         const int slot = (a.exc_mode == 2) ? 0 : (tile & (kExcSlots - 1));
-        const int b = tile & 1;
-        if (a.exc_mode != 2) mbar_wait(&exc_full[slot], (uint32_t)((tile >> 2) & 1));
-        if (tile >= 2) mbar_wait(&ft_free[b], (uint32_t)(((tile >> 1) - 1) & 1));
+        if (a.exc_mode != 2) {
+            if (warp == 0 && tile + 2 < ntiles) publish_exc<T>(a, exc_s, exc_full, tile + 2, m0, gcount, lane);
+            mbar_wait(&exc_full[slot], (uint32_t)((tile / kExcSlots) & 1));
+        }
         if (has_unit) {
-            const T* es = exc_s + (size_t)slot * a.T * a.Gp + tq * U;
-            V* fp = (V*)ft + (size_t)b * tile_vecs + tq * a.pitch + u;
+            core.begin_tile();
+            const T* es = exc_s + slot * a.T * a.Gp + tq * U;
+            V* fp = fwr;
 #pragma unroll 2
-            for (int s = 0; s < steps; ++s, es += a.Gp, fp += step_stride) {
+            for (int s = 0; s < steps; ++s, es += a.Gp, fp += kFtPitch) {
                 const V e = *(const V*)es;
                 bool write_now = false;
                 int64_t dec_base = 0;
@@ -422,11 +442,28 @@ __device__ __forceinline__ void k2_body(const K2Args& a) {
                 }
                 *fp = fv;
             }
-            core.end_tile();
+            if ((tile & 3) == 3) core.end_tile();
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&ft_full[b]);          // release: this warp's part of the tile is written
+        // ---- stage 1: this warp's 4 column parts x 8 step rows -> PT[tile & 3] ----------
+        const int pb = tile & (kPtSlots - 1);
+        if (tile >= kPtSlots) mbar_wait(&pfree[pb], (uint32_t)((tile / kPtSlots - 1) & 1));
+        {
+            V acc = frd[0];
+#pragma unroll
+            for (int i = 1; i < 8; ++i) {
+                const V v = frd[i];
+#pragma unroll
+                for (int j = 0; j < U; ++j) acc.v[j] += v.v[j];
+            }
+            if (part_used) pt[pb * pt_tile + (lane & 7) * a.ptp + pt_col] = acc;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&pfull[pb]);
+        // ---- stage 2 of the previous tile, by one warp in turn ------------------------------
+        if (tile > 0 && warp == (tile - 1) % nwarps) stage2(tile - 1);
     }
+    if (warp == (ntiles - 1) % nwarps) stage2(ntiles - 1);
 
 #pragma unroll
     for (int j = 0; j < U; ++j) {
@@ -438,12 +475,12 @@ __device__ __forceinline__ void k2_body(const K2Args& a) {
 }
 
 template <int FIB, int CENTRAL, int U, bool FORCES>
-__global__ void __launch_bounds__(512, 2) k2_fused_f32(const K2Args a) {
+__global__ void __launch_bounds__(480, 2) k2_fused_f32(const K2Args a) {
     k2_body<CoreF32<FIB, CENTRAL, U>, U, FORCES>(a);
 }
 
 template <int FIB, int CENTRAL, int U, bool FORCES>
-__global__ void __launch_bounds__(512, 1) k2_fused_f64(const K2Args a) {
+__global__ void __launch_bounds__(480, 1) k2_fused_f64(const K2Args a) {
     k2_body<CoreF64<FIB, CENTRAL, U>, U, FORCES>(a);
 }
 

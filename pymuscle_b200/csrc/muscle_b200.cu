@@ -542,7 +542,7 @@ extern "C" int mb_peripheral_fatigue(const MbConfig* cfg, int64_t rows, int64_t 
 
 // ---- fused geometry ---------------------------------------------------------------------
 struct FusedGeom {
-    int U, q, G, Gp, T, P, pitch, ncomp, threads, smem;
+    int U, q, G, Gp, T, ns, npg, ptp, threads, smem;
     int64_t blocks;
 };
 
@@ -551,7 +551,7 @@ static int env_int(const char* name, int dflt) {
     return (v && *v) ? atoi(v) : dflt;
 }
 
-static const int kFusedMaxUnits = 480;     // compute threads per block <= 480, + 1 service warp = 512
+static const int kFusedMaxUnits = 480;     // threads per block <= 480 (15 warps), 2 blocks per SM in FP32 mode
 
 static int fused_geometry(const MbConfig& c, int64_t M, int32_t n, int32_t K, int32_t upt, FusedGeom* g) {
     if (n < 2 || n > kFusedMaxUnits)
@@ -559,7 +559,8 @@ static int fused_geometry(const MbConfig& c, int64_t M, int32_t n, int32_t K, in
     if (M <= 0 || K <= 0) return fail(MB_EINVAL, "M and K must be positive");
     const bool f32 = c.precision == MB_F32;
     const int esz = f32 ? 4 : 8;
-    int q = kFusedMaxUnits / n;
+    const int ns = (n + 7) / 8 * 8;                          // threads per muscle group (stage-1 parts are 8 wide)
+    int q = kFusedMaxUnits / ns;
     if (upt != 0 && upt != 1 && upt != 2 && upt != 4) return fail(MB_EINVAL, "units_per_thread must be 0, 1, 2 or 4");
     if (!f32 && upt == 4) return fail(MB_EINVAL, "units_per_thread 4 is FP32-only");
     int U = upt;
@@ -570,37 +571,19 @@ static int fused_geometry(const MbConfig& c, int64_t M, int32_t n, int32_t K, in
     }
     // a block should not own more muscles than exist
     while (q > 1 && (int64_t)(q - 1) * U >= M) --q;
-    g->U = U; g->q = q; g->G = q * U;
+    g->U = U; g->q = q; g->G = q * U; g->ns = ns; g->npg = ns / 8;
     const int vl = 16 / esz;
     g->Gp = (g->G + vl - 1) / vl * vl;
-    g->ncomp = (q * n + 31) / 32 * 32;
-    g->threads = g->ncomp + 32;                              // + the service warp
+    g->threads = (q * ns + 31) / 32 * 32;
+    const int warps = g->threads / 32;
     const int vec_bytes = U * esz;
-    int T = env_int("MB_FUSED_T", 0);                        // tuning override (steps per tile)
-    if (T <= 0) {
-        T = (64 * 1024) / (2 * q * (n + 8) * vec_bytes);     // both force-tile buffers within ~64 KB
-        if (T > 8) T = 8;
-    }
-    if (T < 1) T = 1;
+    g->ptp = (warps * 4) | 1;                                // odd PT row pitch (vectors)
+    int T = kTile;
     if (T > K) T = K;
     g->T = T;
-    // lanes per (step, q) row in the service warp: fill the warp once if possible
-    int P = env_int("MB_FUSED_P", 0);
-    if (P != 1 && P != 2 && P != 4 && P != 8 && P != 16 && P != 32) {
-        P = 32;
-        while (P > 1 && (T * q * P > 32 || P > n)) P >>= 1;
-    }
-    g->P = P;
-    // row pitch in vectors: for 16-byte vectors make pitch == P (mod 8) so that the 8 lanes of a
-    // quarter-warp (8/P rows x P parts, or 8 rows when P == 1) hit 8 different 16-byte bank groups
-    int pitch = n;
-    if (vec_bytes == 16 && P <= 8) {
-        const int want = P % 8;
-        while (pitch % 8 != want) ++pitch;
-    }
-    g->pitch = pitch;
-    g->smem = 64 + 4 * T * g->Gp * esz + 2 * T * q * pitch * vec_bytes;
-    if (g->smem > 110 * 1024) return fail(MB_EUNSUPPORTED, "fused kernel: tile does not fit in shared memory");
+    g->smem = 128 + kExcSlots * T * g->Gp * esz + warps * kTile * kFtPitch * vec_bytes +
+              kPtSlots * kTile * g->ptp * vec_bytes;
+    if (g->smem > 220 * 1024) return fail(MB_EUNSUPPORTED, "fused kernel: tile does not fit in shared memory");
     g->blocks = (M + g->G - 1) / g->G;
     return MB_OK;
 }
@@ -619,7 +602,7 @@ extern "C" int mb_fused_geometry(const MbConfig* cfg, int64_t M, int32_t n, int3
 
 template <typename KernelT>
 static int launch_fused(KernelT kernel, const K2Args& a, const FusedGeom& g, cudaStream_t st) {
-    if (g.smem > 48 * 1024)
+    if (g.smem > 48 * 1024)   // opt in to large dynamic shared memory (cheap; set on every launch)
         MB_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem));
     kernel<<<(unsigned)g.blocks, g.threads, g.smem, st>>>(a);
     MB_CUDA_OK(cudaGetLastError());
@@ -657,8 +640,8 @@ extern "C" int mb_step_fused(const MbConfig* cfg, const void* params_dev, int64_
 
     K2Args a;
     memset(&a, 0, sizeof(a));
-    a.params = params_dev; a.M = M; a.n = n; a.q = g.q; a.K = K; a.T = g.T; a.P = g.P; a.G = g.G; a.Gp = g.Gp;
-    a.pitch = g.pitch; a.ncomp = g.ncomp;
+    a.params = params_dev; a.M = M; a.n = n; a.ns = g.ns; a.q = g.q; a.K = K; a.T = g.T; a.G = g.G; a.Gp = g.Gp;
+    a.npg = g.npg; a.ptp = g.ptp;
     a.exc = exc_dev; a.exc_stride_k = exc_stride_k;
     if (exc_stride_k == 0) {
         a.exc_mode = 2;
@@ -675,6 +658,7 @@ extern "C" int mb_step_fused(const MbConfig* cfg, const void* params_dev, int64_
     a.dt = step_size;
     a.adk_d = -kLog2e / cfg->adaptation_time_constant;
     a.max_dur = cfg->max_duration;
+    a.decay_d = std::exp(-step_size / cfg->adaptation_time_constant);
     a.sf = scal_f(*cfg);
     a.sd = scal_d(*cfg);
 
