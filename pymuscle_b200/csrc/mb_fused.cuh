@@ -5,7 +5,11 @@
 // multiple of 8; thread tq*ns + u handles unit u of muscles tq*U .. +U-1: its U
 // unit-instances share one set of per-unit parameters (registers, loaded once per window
 // as 128-bit vectors) and give U independent dependency chains.  Per step: one vector LDS
-// (U excitations), the arithmetic of mb_core.cuh, one vector STS (U forces).
+// (U excitations), the arithmetic below, one vector STS (U forces).
+//
+// FP32 mode packs two instances into one 64-bit register pair and uses the sm_100 packed
+// FP32 instructions (FFMA2 / FMUL2 / FADD2, one issue slot for two lanes of FMA-pipe work);
+// compares, min/max and selects stay scalar (ALU pipe), ex2 is one MUFU per instance-step.
 //
 // Per-(step, muscle) totals without any block-wide barrier.  Time is cut into tiles of
 // T = 8 steps and the sum over a muscle's units is done in two stages:
@@ -16,15 +20,15 @@
 //            8 independent 128-bit LDS (bank-conflict free) and stores the partial into
 //            PT[tile & 3][s][4*warp + part].  Group boundaries are multiples of 8 threads, so
 //            every 8-column part belongs to exactly one muscle group.
-//   stage 2  one warp per tile (rotating: warp (tile % warps)) waits on the mbarrier that
-//            counts the warps' stage-1 arrivals, sums the ns/8 partials of every
-//            (step, muscle) and stores the totals to HBM (coalesced).
+//   stage 2  one warp per tile (rotating) waits on the mbarrier that counts the warps'
+//            stage-1 arrivals, sums the ns/8 partials of every (step, muscle) and stores the
+//            totals to HBM (coalesced).
 //
 // PT is a ring of 4 tiles guarded by mbarriers (pfull: 1 arrival per warp; pfree: 1 arrival
-// by the stage-2 warp), so warps may drift up to 3 tiles apart and never wait for each
-// other in steady state.  Warp 0 additionally stages the per-step excitations two tiles
-// ahead with cp.async.bulk (1-D bulk copy per step row, mbarrier complete_tx) into an
-// 8-slot ring; consumers wait on the slot's mbarrier.
+// by the stage-2 warp), so warps may drift up to 4 tiles apart and never wait for each
+// other in steady state.  Warp 0 additionally stages the per-step excitations kExcAhead
+// tiles ahead with cp.async.bulk (1-D bulk copy per step row, mbarrier complete_tx) into a
+// 16-slot ring; consumers wait on the slot's mbarrier.
 //
 // HBM traffic per window: state in/out (32 B/unit) plus excitations and totals
 // (2*sizeof(T)/n B per unit-step) -- see DESIGN.md.
@@ -33,7 +37,8 @@
 
 namespace mb {
 
-constexpr int kExcSlots = 8;     // excitation ring (tiles)
+constexpr int kExcSlots = 16;    // excitation ring (tiles)
+constexpr int kExcAhead = 6;     // tiles staged ahead of the staging warp's own position (> PT drift bound)
 constexpr int kPtSlots = 4;      // partial-sum ring (tiles)
 constexpr int kTile = 8;         // steps per tile (stage 1 maps lane & 7 to the step)
 constexpr int kFtPitch = 33;     // row pitch of a warp's force tile, in vectors (odd => conflict free)
@@ -56,22 +61,24 @@ struct K2Args {
     int32_t peripheral;
     double dt, adk_d, max_dur;
     double decay_d;              // exp(-dt/tau): per-step factor of exp(-dur/tau) for a firing unit
+    float dtk;                   // (float)(dt * adk_d)
+    float decay, dm1;            // (float)decay_d and decay - 1 (exact in float)
     ScalF sf;
     ScalD sd;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done;
     do {
         asm volatile(
@@ -81,20 +88,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             "selp.u32 %0, 1, 0, p;\n"
             "}\n"
             : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
+            : "r"(bar), "r"(parity)
             : "memory");
     } while (!done);
 }
 // 1-D bulk async copy global -> shared (SASS UBLKCP); bytes % 16 == 0, both addresses 16-B aligned.
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
 
 // U-wide vector of T in shared memory (one LDS/STS of 4*U or 8*U bytes)
 template <typename T, int U> struct alignas(sizeof(T) * U) VecU { T v[U]; };
+
+__device__ __forceinline__ float2 bc(float x) { return make_float2(x, x); }   // broadcast operand of a packed op
 
 // ======================================================================================
 // Per-thread arithmetic of the two precision modes.  Each "core" holds the unit's
@@ -102,112 +110,175 @@ template <typename T, int U> struct alignas(sizeof(T) * U) VecU { T v[U]; };
 // ======================================================================================
 
 // ---- FP32 mode ------------------------------------------------------------------------
-// Capacity is carried as hi + lo (two floats): `hi` is frozen for a tile, per-step
-// decrements accumulate in the small `lo` (so their rounding error is relative to the
-// tile's decrement, not to the capacity) and the pair is renormalised (error-free
-// TwoSum) once per tile.  On-duration is dur0 + count*dt with an exact float step
+// Instances are processed in pairs (x = instance 2p, y = instance 2p+1 of a float2).
+//
+// Capacity is carried as hi + lo (two floats): `hi` is frozen between renormalisations,
+// per-step decrements accumulate in the small `lo` (so their rounding error is relative to
+// the accumulated decrement, not to the capacity) and the pair is renormalised (error-free
+// TwoSum) every 4th tile.  On-duration is dur0 + count*dt with an exact float step
 // counter.  Plain float accumulators miss rtol 1e-4 over 10,000 steps.
 //
 // CENTRAL: 0 = pool.apply_fatigue off (adaptation is the identity)
 //          1 = on, fast path: the launcher has checked that (a) the adaptation of a
 //              recruited unit cannot be negative and (b) max_duration/tau is so large
 //              that the duration clamp cannot change exp(-dur/tau); both clamps drop out.
-//              E = exp(-dur/tau) is carried by recurrence -- a firing step multiplies it by
-//              exp(-dt/tau) -- and re-synchronised with one ex2 per tile from the exact
-//              counter, which replaces the per-step MUFU of the adaptation curve
+//              nD = exp(-dur/tau) - 1 is carried by recurrence -- a firing step maps it to
+//              nD*decay + (decay - 1) -- and re-synchronised with one ex2 per tile from the
+//              exact counter, which replaces the per-step MUFU of the adaptation curve
 //          2 = on, general path with both clamps (pool:202-206, :221)
 template <int FIB, int CENTRAL, int U>
 struct CoreF32 {
     using T = float;
+    using V = VecU<float, U>;
     static constexpr bool kCentral = CENTRAL != 0;
-    using ParamVec = float4;
+    static constexpr int NP = (U + 1) / 2;           // pairs
     UnitF p;
     ScalF sc;
-    float fatdt, rdidt, dtk, decay;
-    float hi[U], lo[U], cpf[U], cnt[U], arg0[U], room[U], E[U];
+    float fatdt, rdidt, dtk, decay, dm1;
+    float2 hi[NP], lo[NP], cpf[NP], cnt[NP], nD[NP], room[NP];
+    float arg0[2 * NP];
+
+    static __device__ __forceinline__ float& el(float2& v, int k) { return k ? v.y : v.x; }
 
     __device__ __forceinline__ void load(const K2Args& a, int u) {
         p = load_unit((const float4*)a.params, a.n, u);
         sc = a.sf;
         fatdt = a.peripheral ? (float)((double)p.fat * a.dt) : 0.0f;
         rdidt = a.peripheral ? (float)((double)p.rdi * a.dt) : 0.0f;
-        dtk = (float)(a.dt * a.adk_d);
-        decay = (float)a.decay_d;
+        dtk = a.dtk;
+        decay = a.decay;
+        dm1 = a.dm1;
+#pragma unroll
+        for (int j = 0; j < 2 * NP; ++j) init(j, a, rest_capacity(), 0.0);   // the idle half of an odd U
     }
     __device__ __forceinline__ double rest_capacity() const { return (double)p.ptf + (double)p.ptf_lo; }
     __device__ __forceinline__ void init(int j, const K2Args& a, double c, double d0) {
-        hi[j] = (float)c;
-        lo[j] = (float)(c - (double)hi[j]);
-        cpf[j] = hi[j] + lo[j];
-        room[j] = (p.ptf - hi[j]) + p.ptf_lo;            // peak - hi: the upper bound of lo (pmf:104-105)
-        cnt[j] = 0.0f;
+        const int pi = j >> 1, k = j & 1;
+        const float h = (float)c;
+        const float l = (float)(c - (double)h);
+        el(hi[pi], k) = h;
+        el(lo[pi], k) = l;
+        el(cpf[pi], k) = h + l;
+        el(room[pi], k) = (p.ptf - h) + p.ptf_lo;        // peak - hi: the upper bound of lo (pmf:104-105)
+        el(cnt[pi], k) = 0.0f;
+        el(nD[pi], k) = 0.0f;
         arg0[j] = (float)(d0 * a.adk_d);
-        E[j] = 1.0f;
     }
     __device__ __forceinline__ void begin_tile() {
         if (CENTRAL == 1) {
 #pragma unroll
-            for (int j = 0; j < U; ++j) E[j] = ex2_approx(fmaf(cnt[j], dtk, arg0[j]));
+            for (int j = 0; j < 2 * NP; ++j)
+                el(nD[j >> 1], j & 1) = ex2_approx(fmaf(el(cnt[j >> 1], j & 1), dtk, arg0[j])) - 1.0f;
         }
     }
-    // one step of instance j; returns the unit force
-    __device__ __forceinline__ float step(int j, float e, bool& on) {
-        const float r = pool_rate_raw(p, sc, e, on);
-        float fr;
+
+    // one step of the pair pi; x = the two excitations; returns the two unit forces
+    __device__ __forceinline__ float2 step_pair(int pi, float2 x, bool& on_a, bool& on_b) {
+        // ---- pool: rate and recruitment (pool:150-179) ----
+        float2 r = __ffma2_rn(x, bc(sc.gain_e), bc(-p.thr_g));
+        on_a = x.x >= p.crit;
+        on_b = x.y >= p.crit;
+        r.x = fminf(r.x, p.peak);
+        r.y = fminf(r.y, p.peak);
+        float2 fr;
         if (CENTRAL == 0) {
-            fr = on ? r : 0.0f;
+            fr = r;
         } else if (CENTRAL == 1) {
-            const float q = fmaf(r, p.phir, -p.phir6);                     // pool:231-232
-            fr = r - fmaf(-q, E[j], q);                                    // pool:217-221, :121 (dur BEFORE the update)
-            fr = on ? fr : 0.0f;
-            if (on) {                                                      // pool:196-197
-                cnt[j] += 1.0f;
-                E[j] *= decay;
+            const float2 q = __ffma2_rn(r, bc(p.phir), bc(-p.phir6));       // pool:231-232
+            fr = __ffma2_rn(q, nD[pi], r);                                  // r - q*(1 - exp(-dur/tau)), dur BEFORE the update
+            if (on_a) {                                                     // pool:196-197
+                cnt[pi].x += 1.0f;
+                nD[pi].x = fmaf(nD[pi].x, decay, dm1);
+            }
+            if (on_b) {
+                cnt[pi].y += 1.0f;
+                nD[pi].y = fmaf(nD[pi].y, decay, dm1);
             }
         } else {
-            float arg = fmaf(cnt[j], dtk, arg0[j]);
-            if (on) cnt[j] += 1.0f;
-            arg = fmaxf(arg, sc.argmin);
-            const float r0 = on ? r : 0.0f;
-            fr = r0 - fmaxf(pool_adaptation(p, r0, arg), 0.0f);
+            float2 arg = __ffma2_rn(cnt[pi], bc(dtk), make_float2(arg0[2 * pi], arg0[2 * pi + 1]));
+            if (on_a) cnt[pi].x += 1.0f;
+            if (on_b) cnt[pi].y += 1.0f;
+            const float ra = on_a ? r.x : 0.0f, rb = on_b ? r.y : 0.0f;
+            fr.x = ra - fmaxf(pool_adaptation(p, ra, fmaxf(arg.x, sc.argmin)), 0.0f);
+            fr.y = rb - fmaxf(pool_adaptation(p, rb, fmaxf(arg.y, sc.argmin)), 0.0f);
         }
-        float nf;
-        const float F = fibers_force(p, sc, fr, cpf[j], nf);
-        // capacity update on the compensated pair (fibers:110-114, pmf:94-105)
-        float l = fmaf(nf, -fatdt, lo[j]);
+        fr.x = on_a ? fr.x : 0.0f;                                          // pool:171-172
+        fr.y = on_b ? fr.y : 0.0f;
+        // ---- fibers (fibers:211-259) on ny = -kappa*x: exp(-2x^3) = ex2(ny^3) ----
+        const float2 ctkn = __ffma2_rn(cpf[pi], bc(p.ctB), bc(-p.ctA));     // -kappa*ct_cur/1000
+        const float2 ny = __fmul2_rn(ctkn, fr);
+        const float2 lin = __fmul2_rn(ny, bc(-sc.c25k));
+        const float2 y2 = __fmul2_rn(ny, ny);
+        const float2 ny3 = __fmul2_rn(y2, ny);
+        float2 ex;
+        ex.x = ex2_approx(ny3.x);
+        ex.y = ex2_approx(ny3.y);
+        const float2 sig = __ffma2_rn(ex, bc(-1.0f), bc(1.0f));
+        float2 nf;
+        nf.x = (ny.x >= -sc.ythr) ? lin.x : sig.x;                          // x <= 0.4 (fibers:233-236)
+        nf.y = (ny.y >= -sc.ythr) ? lin.y : sig.y;
+        const float2 F = __fmul2_rn(nf, cpf[pi]);                           // fibers:258 (capacity BEFORE the update)
+        // ---- capacity update on the compensated pair (fibers:110-114, pmf:94-105) ----
+        float2 l = __ffma2_rn(nf, bc(-fatdt), lo[pi]);
         if (FIB == MB_FIBERS_PYMUSCLE) {
-            const float gap = room[j] - lo[j];                             // peak - capacity
-            l = fmaf((nf <= 0.0f) ? gap : 0.0f, rdidt, l);                 // pmf:121-141
+            const float2 gap = __fadd2_rn(room[pi], make_float2(-lo[pi].x, -lo[pi].y));   // peak - capacity
+            float2 g;
+            g.x = (nf.x <= 0.0f) ? gap.x : 0.0f;                            // pmf:121-141
+            g.y = (nf.y <= 0.0f) ? gap.y : 0.0f;
+            l = __ffma2_rn(g, bc(rdidt), l);
         }
-        l = fmaxf(l, -hi[j]);
-        if (FIB == MB_FIBERS_PYMUSCLE) l = fminf(l, room[j]);
-        lo[j] = l;
-        cpf[j] = hi[j] + l;
+        l.x = fmaxf(l.x, -hi[pi].x);
+        l.y = fmaxf(l.y, -hi[pi].y);
+        if (FIB == MB_FIBERS_PYMUSCLE) {
+            l.x = fminf(l.x, room[pi].x);
+            l.y = fminf(l.y, room[pi].y);
+        }
+        lo[pi] = l;
+        cpf[pi] = __fadd2_rn(hi[pi], l);
         return F;
     }
-    // renormalise (TwoSum) so that |lo| <= ulp(hi)/2 again
-    __device__ __forceinline__ void end_tile() {
+
+    // one step of all U instances: e -> f (forces); onbits = recruitment mask of the instances
+    __device__ __forceinline__ void step_vec(const V& e, V& f, unsigned& onbits) {
+        onbits = 0;
 #pragma unroll
-        for (int j = 0; j < U; ++j) {
-            const float s1 = hi[j] + lo[j];
-            const float bb = s1 - hi[j];
-            const float err = (hi[j] - (s1 - bb)) + (lo[j] - bb);
-            hi[j] = s1;
-            lo[j] = err;
-            room[j] = (p.ptf - s1) + p.ptf_lo;
+        for (int pi = 0; pi < NP; ++pi) {
+            const int j0 = 2 * pi, j1 = (2 * pi + 1 < U) ? 2 * pi + 1 : 2 * pi;
+            bool oa, ob;
+            const float2 F = step_pair(pi, make_float2(e.v[j0], e.v[j1]), oa, ob);
+            f.v[j0] = F.x;
+            if (2 * pi + 1 < U) f.v[j1] = F.y;
+            onbits |= (oa ? 1u : 0u) << j0;
+            if (2 * pi + 1 < U) onbits |= (ob ? 1u : 0u) << j1;
+        }
+    }
+
+    // renormalise (TwoSum) so that |lo| <= ulp(hi)/2 again
+    __device__ __forceinline__ void renormalise() {
+#pragma unroll
+        for (int pi = 0; pi < NP; ++pi) {
+            const float2 s1 = __fadd2_rn(hi[pi], lo[pi]);
+            const float2 bb = __fadd2_rn(s1, make_float2(-hi[pi].x, -hi[pi].y));
+            const float2 t1 = __fadd2_rn(s1, make_float2(-bb.x, -bb.y));
+            const float2 e1 = __fadd2_rn(hi[pi], make_float2(-t1.x, -t1.y));
+            const float2 e2 = __fadd2_rn(lo[pi], make_float2(-bb.x, -bb.y));
+            hi[pi] = s1;
+            lo[pi] = __fadd2_rn(e1, e2);
+            room[pi] = __fadd2_rn(__fadd2_rn(bc(p.ptf), make_float2(-s1.x, -s1.y)), bc(p.ptf_lo));
         }
     }
     __device__ __forceinline__ void store(int j, const K2Args& a, int64_t idx) {
+        const int pi = j >> 1, k = j & 1;
         if (a.peripheral) {
             // add the window's change to the float64 state: an untouched unit keeps its
             // exact bits, and the low bits of the incoming capacity are not truncated
             const double c0 = a.cpf[idx];
             const float h0 = (float)c0;
             const float l0 = (float)(c0 - (double)h0);
-            a.cpf[idx] = c0 + (((double)hi[j] - (double)h0) + ((double)lo[j] - (double)l0));
+            a.cpf[idx] = c0 + (((double)el(hi[pi], k) - (double)h0) + ((double)el(lo[pi], k) - (double)l0));
         }
         if (CENTRAL) {
-            double d = fma((double)cnt[j], a.dt, a.dur[idx]);
+            double d = fma((double)el(cnt[pi], k), a.dt, a.dur[idx]);
             d = (d > a.max_dur) ? a.max_dur : d;
             a.dur[idx] = (d < 0.0) ? 0.0 : d;
         }
@@ -223,8 +294,8 @@ struct CoreF32 {
 template <int FIB, int CENTRAL, int U>
 struct CoreF64 {
     using T = double;
+    using V = VecU<double, U>;
     static constexpr bool kCentral = CENTRAL != 0;
-    using ParamVec = double2;
     UnitD p;
     ScalD sc;
     double fatdt, rdidt, dt, max_dur, decay, Emax;
@@ -239,6 +310,8 @@ struct CoreF64 {
         max_dur = a.max_dur;
         decay = a.decay_d;
         Emax = CENTRAL ? exp(a.max_dur * a.sd.mitau) : 0.0;
+#pragma unroll
+        for (int j = 0; j < U; ++j) init(j, a, p.ptf, 0.0);                // instances beyond the batch rest
     }
     __device__ __forceinline__ double rest_capacity() const { return p.ptf; }
     __device__ __forceinline__ void init(int j, const K2Args&, double c, double d0) {
@@ -271,7 +344,16 @@ struct CoreF64 {
         cpf[j] = fatigue_update<FIB == MB_FIBERS_PYMUSCLE>(cpf[j], nf, fatdt, rdidt, p.ptf);
         return F;
     }
-    __device__ __forceinline__ void end_tile() {}
+    __device__ __forceinline__ void step_vec(const V& e, V& f, unsigned& onbits) {
+        onbits = 0;
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            bool on;
+            f.v[j] = step(j, e.v[j], on);
+            onbits |= (on ? 1u : 0u) << j;
+        }
+    }
+    __device__ __forceinline__ void renormalise() {}
     __device__ __forceinline__ void store(int j, const K2Args& a, int64_t idx) {
         if (a.peripheral) a.cpf[idx] = cpf[j];
         if (CENTRAL) a.dur[idx] = dur[j];
@@ -280,23 +362,25 @@ struct CoreF64 {
 };
 
 // ======================================================================================
-// excitation staging (warp 0): tile `tile` of the window -> ring slot tile & 7
+// excitation staging (warp 0): tile `tile` of the window -> ring slot tile & 15
 // ======================================================================================
 template <typename T>
-__device__ __forceinline__ void publish_exc(const K2Args& a, T* exc_s, uint64_t* exc_full, int tile, int64_t m0,
+__device__ __forceinline__ void publish_exc(const K2Args& a, T* exc_s, uint32_t exc_bar0, int tile, int64_t m0,
                                             int gcount, int lane) {
     const int k0 = tile * a.T;
     const int steps = min(a.T, a.K - k0);
     const int slot = tile & (kExcSlots - 1);
     T* dst = exc_s + slot * a.T * a.Gp;
     const T* src = (const T*)a.exc + (int64_t)k0 * a.exc_stride_k + m0;
+    const uint32_t bar = exc_bar0 + 8u * slot;
     if (a.exc_mode == 0) {
         if (lane == 0) {
             const uint32_t row_bytes = (uint32_t)(gcount * sizeof(T));
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_expect_tx(&exc_full[slot], row_bytes * steps);
+            mbar_expect_tx(bar, row_bytes * steps);
+            const uint32_t d0 = smem_u32(dst);
             for (int s = 0; s < steps; ++s)
-                bulk_g2s(dst + s * a.Gp, src + (int64_t)s * a.exc_stride_k, row_bytes, &exc_full[slot]);
+                bulk_g2s(d0 + s * a.Gp * (int)sizeof(T), src + (int64_t)s * a.exc_stride_k, row_bytes, bar);
         }
     } else {
         for (int i = lane; i < steps * a.G; i += 32) {
@@ -304,7 +388,7 @@ __device__ __forceinline__ void publish_exc(const K2Args& a, T* exc_s, uint64_t*
             if (g < gcount) dst[s * a.Gp + g] = __ldg(src + (int64_t)s * a.exc_stride_k + g);
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&exc_full[slot]);
+        if (lane == 0) mbar_arrive(bar);
     }
 }
 
@@ -316,10 +400,11 @@ __device__ __forceinline__ void k2_body(const K2Args& a) {
     using T = typename Core::T;
     using V = VecU<T, U>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t* exc_full = (uint64_t*)smem_raw;            // [8]
-    uint64_t* pfull = exc_full + kExcSlots;              // [4]  stage-1 partials of a tile complete
-    uint64_t* pfree = pfull + kPtSlots;                  // [4]  stage 2 has consumed them
-    T* exc_s = (T*)(smem_raw + 128);                     // [8][T][Gp]
+    // mbarriers: exc_full[16] | pfull[4] (stage-1 partials of a tile complete) | pfree[4] (stage 2 consumed them)
+    const uint32_t exc_bar0 = smem_u32(smem_raw);
+    const uint32_t pfull0 = exc_bar0 + 8u * kExcSlots;
+    const uint32_t pfree0 = pfull0 + 8u * kPtSlots;
+    T* exc_s = (T*)(smem_raw + 256);                     // [16][T][Gp]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     V* ft = (V*)(exc_s + kExcSlots * a.T * a.Gp);        // [nwarps][kTile][kFtPitch]
     V* pt = ft + nwarps * kTile * kFtPitch;              // [4][kTile][ptp]
@@ -331,10 +416,10 @@ __device__ __forceinline__ void k2_body(const K2Args& a) {
     const int ntiles = (a.K + a.T - 1) / a.T;
 
     if (tid == 0) {
-        for (int i = 0; i < kExcSlots; ++i) mbar_init(&exc_full[i], 1);
+        for (int i = 0; i < kExcSlots; ++i) mbar_init(exc_bar0 + 8u * i, 1);
         for (int i = 0; i < kPtSlots; ++i) {
-            mbar_init(&pfull[i], nwarps);
-            mbar_init(&pfree[i], 1);
+            mbar_init(pfull0 + 8u * i, nwarps);
+            mbar_init(pfree0 + 8u * i, 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -353,7 +438,7 @@ __device__ __forceinline__ void k2_body(const K2Args& a) {
         }
         __syncthreads();
     } else if (warp == 0) {
-        for (int t = 0; t < min(2, ntiles); ++t) publish_exc<T>(a, exc_s, exc_full, t, m0, gcount, lane);
+        for (int t = 0; t < min(kExcAhead, ntiles); ++t) publish_exc<T>(a, exc_s, exc_bar0, t, m0, gcount, lane);
     }
 
     const int tq = tid / a.ns;
@@ -362,24 +447,19 @@ __device__ __forceinline__ void k2_body(const K2Args& a) {
     const int u = has_unit ? u_raw : 0;
     Core core;
     core.load(a, u);
-
-    T F[U];
-    bool valid[U];
 #pragma unroll
     for (int j = 0; j < U; ++j) {
         const int g = tq * U + j;
-        valid[j] = has_unit && g < gcount;
-        const int64_t idx = (m0 + g) * n + u;
-        const double c = valid[j] ? a.cpf[idx] : core.rest_capacity();
-        const double d0 = (valid[j] && Core::kCentral) ? a.dur[idx] : 0.0;
-        core.init(j, a, c, d0);
-        F[j] = 0;
+        if (has_unit && g < gcount) {
+            const int64_t idx = (m0 + g) * n + u;
+            core.init(j, a, a.cpf[idx], Core::kCentral ? a.dur[idx] : 0.0);
+        }
     }
 
     // stage 2: totals of tile `t` from the partials PT[t & 3]; executed by one whole warp
     auto stage2 = [&](int t) {
         const int pb = t & (kPtSlots - 1);
-        mbar_wait(&pfull[pb], (uint32_t)((t / kPtSlots) & 1));
+        mbar_wait(pfull0 + 8u * pb, (uint32_t)((t / kPtSlots) & 1));
         if (a.totals) {
             const int k0 = t * a.T;
             const int steps = min(a.T, a.K - k0);
@@ -390,64 +470,64 @@ __device__ __forceinline__ void k2_body(const K2Args& a) {
                 const int tqo = g / U, j = g - tqo * U;
                 const T* src = pp + (s * a.ptp + tqo * a.npg) * U + j;
                 T acc = src[0];
+#pragma unroll 5
                 for (int q2 = 1; q2 < a.npg; ++q2) acc += src[q2 * U];
                 if (g < gcount) totals[(int64_t)(k0 + s) * a.totals_stride_k + m0 + g] = core.out_scale(acc);
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&pfree[pb]);
+        if (lane == 0) mbar_arrive(pfree0 + 8u * pb);
     };
 
-    V* ftw = ft + warp * (kTile * kFtPitch);              // this warp's force tile
-    V* const fwr = ftw + lane;                            // compute: row s at fwr + s*kFtPitch
-    const V* const frd = ftw + (lane & 7) * kFtPitch + (lane >> 3) * 8;   // stage 1: row lane&7, part lane>>3
-    const int pt_col = warp * 4 + (lane >> 3);
-    const bool part_used = pt_col < a.q * a.npg;
+    V* const fwr = ft + warp * (kTile * kFtPitch) + lane;                                   // compute: row s at fwr + s*kFtPitch
+    const V* const frd = ft + warp * (kTile * kFtPitch) + (lane & 7) * kFtPitch + (lane >> 3) * 8;   // stage 1
+    V* const pwr = pt + (lane & 7) * a.ptp + warp * 4 + (lane >> 3);                        // + pb*pt_tile
+    const bool part_used = warp * 4 + (lane >> 3) < a.q * a.npg;
+    const T* const es0 = exc_s + tq * U;
+    int s2warp = 0;                                       // the warp that runs stage 2 of tile-1 this iteration: (tile-1) % nwarps
 
     for (int tile = 0; tile < ntiles; ++tile) {
         const int k0 = tile * a.T;
         const int steps = min(a.T, a.K - k0);
-        const int slot = (a.exc_mode == 2) ? 0 : (tile & (kExcSlots - 1));
+        int slot = 0;
         if (a.exc_mode != 2) {
-            if (warp == 0 && tile + 2 < ntiles) publish_exc<T>(a, exc_s, exc_full, tile + 2, m0, gcount, lane);
-            mbar_wait(&exc_full[slot], (uint32_t)((tile / kExcSlots) & 1));
+            slot = tile & (kExcSlots - 1);
+            if (warp == 0 && tile + kExcAhead < ntiles)
+                publish_exc<T>(a, exc_s, exc_bar0, tile + kExcAhead, m0, gcount, lane);
+            mbar_wait(exc_bar0 + 8u * slot, (uint32_t)((tile / kExcSlots) & 1));
         }
         if (has_unit) {
             core.begin_tile();
-            const T* es = exc_s + slot * a.T * a.Gp + tq * U;
+            const T* es = es0 + slot * a.T * a.Gp;
             V* fp = fwr;
 #pragma unroll 2
             for (int s = 0; s < steps; ++s, es += a.Gp, fp += kFtPitch) {
                 const V e = *(const V*)es;
-                bool write_now = false;
-                int64_t dec_base = 0;
+                V fv;
+                unsigned onbits;
+                core.step_vec(e, fv, onbits);
+                *fp = fv;
                 if (FORCES) {
                     const int k = k0 + s;
-                    write_now = ((k + 1) % a.forces_every) == 0;
-                    dec_base = (int64_t)(k / a.forces_every) * a.M * n;
-                }
-                V fv;
+                    if (((k + 1) % a.forces_every) == 0) {
+                        const int64_t dec_base = (int64_t)(k / a.forces_every) * a.M * n;
 #pragma unroll
-                for (int j = 0; j < U; ++j) {
-                    bool on;
-                    F[j] = core.step(j, e.v[j], on);
-                    fv.v[j] = F[j];
-                    if (FORCES) {
-                        if (write_now && valid[j]) {
-                            const int64_t idx = dec_base + (m0 + tq * U + j) * n + u;
-                            ((T*)a.forces_dec)[idx] = F[j];
-                            if (a.mask_dec) a.mask_dec[idx] = on ? 1 : 0;
+                        for (int j = 0; j < U; ++j) {
+                            if (tq * U + j < gcount) {
+                                const int64_t idx = dec_base + (m0 + tq * U + j) * n + u;
+                                ((T*)a.forces_dec)[idx] = fv.v[j];
+                                if (a.mask_dec) a.mask_dec[idx] = (uint8_t)((onbits >> j) & 1u);
+                            }
                         }
                     }
                 }
-                *fp = fv;
             }
-            if ((tile & 3) == 3) core.end_tile();
+            if ((tile & 3) == 3) core.renormalise();
         }
         __syncwarp();
         // ---- stage 1: this warp's 4 column parts x 8 step rows -> PT[tile & 3] ----------
         const int pb = tile & (kPtSlots - 1);
-        if (tile >= kPtSlots) mbar_wait(&pfree[pb], (uint32_t)((tile / kPtSlots - 1) & 1));
+        if (tile >= kPtSlots) mbar_wait(pfree0 + 8u * pb, (uint32_t)((tile / kPtSlots - 1) & 1));
         {
             V acc = frd[0];
 #pragma unroll
@@ -456,21 +536,29 @@ __device__ __forceinline__ void k2_body(const K2Args& a) {
 #pragma unroll
                 for (int j = 0; j < U; ++j) acc.v[j] += v.v[j];
             }
-            if (part_used) pt[pb * pt_tile + (lane & 7) * a.ptp + pt_col] = acc;
+            if (part_used) pwr[pb * pt_tile] = acc;
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&pfull[pb]);
+        if (lane == 0) mbar_arrive(pfull0 + 8u * pb);
         // ---- stage 2 of the previous tile, by one warp in turn ------------------------------
-        if (tile > 0 && warp == (tile - 1) % nwarps) stage2(tile - 1);
+        if (tile > 0) {
+            if (warp == s2warp) stage2(tile - 1);
+            if (++s2warp == nwarps) s2warp = 0;
+        }
     }
-    if (warp == (ntiles - 1) % nwarps) stage2(ntiles - 1);
+    if (warp == s2warp) stage2(ntiles - 1);
 
+    if (has_unit) {
+        const int last_row = (a.K - 1) - (ntiles - 1) * a.T;
+        const V fl = fwr[last_row * kFtPitch];            // this lane's forces of the window's last step
 #pragma unroll
-    for (int j = 0; j < U; ++j) {
-        if (!valid[j]) continue;
-        const int64_t idx = (m0 + tq * U + j) * n + u;
-        core.store(j, a, idx);
-        if (a.forces_last) ((T*)a.forces_last)[idx] = F[j];
+        for (int j = 0; j < U; ++j) {
+            const int g = tq * U + j;
+            if (g >= gcount) continue;
+            const int64_t idx = (m0 + g) * n + u;
+            core.store(j, a, idx);
+            if (a.forces_last) ((T*)a.forces_last)[idx] = fl.v[j];
+        }
     }
 }
 

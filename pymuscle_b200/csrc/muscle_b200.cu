@@ -581,7 +581,7 @@ static int fused_geometry(const MbConfig& c, int64_t M, int32_t n, int32_t K, in
     int T = kTile;
     if (T > K) T = K;
     g->T = T;
-    g->smem = 128 + kExcSlots * T * g->Gp * esz + warps * kTile * kFtPitch * vec_bytes +
+    g->smem = 256 + kExcSlots * T * g->Gp * esz + warps * kTile * kFtPitch * vec_bytes +
               kPtSlots * kTile * g->ptp * vec_bytes;
     if (g->smem > 220 * 1024) return fail(MB_EUNSUPPORTED, "fused kernel: tile does not fit in shared memory");
     g->blocks = (M + g->G - 1) / g->G;
@@ -659,6 +659,9 @@ extern "C" int mb_step_fused(const MbConfig* cfg, const void* params_dev, int64_
     a.adk_d = -kLog2e / cfg->adaptation_time_constant;
     a.max_dur = cfg->max_duration;
     a.decay_d = std::exp(-step_size / cfg->adaptation_time_constant);
+    a.dtk = (float)(a.dt * a.adk_d);
+    a.decay = (float)a.decay_d;
+    a.dm1 = a.decay - 1.0f;                                  // exact in float (Sterbenz)
     a.sf = scal_f(*cfg);
     a.sd = scal_d(*cfg);
 
