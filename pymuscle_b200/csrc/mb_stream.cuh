@@ -1,0 +1,233 @@
+// mb_stream.cuh -- K1s: the single-step kernel as an HBM streaming pipeline.
+//
+// The per-step state (capacities, and on-durations when central fatigue is on) is the
+// only HBM traffic that matters: 8 B in / 8 B out per unit per state array plus the
+// 4-8 B force write.  Arithmetic per byte is low, so the kernel is organised around
+// keeping enough bytes in flight rather than around occupancy:
+//
+//   producer warp   walks the block's work list -- (muscle segment, chunk of R rows), cut
+//                   into column tiles of W units -- and copies each tile's state rows
+//                   global -> shared with cp.async.bulk (one bulk copy per row, issued by
+//                   lane r; SASS UBLKCP), completion counted on the stage's `full` mbarrier
+//                   (expect_tx).  NS stages deep: (NS-1) * R * W * 8 B per state array are
+//                   in flight per block regardless of what the consumer warps are doing.
+//   consumer warps  thread tx owns unit u0 + tx of the tile in all R rows: it loads the
+//                   unit's packed parameters once (L2), waits for the stage, reads its R
+//                   state values from shared memory, runs the step arithmetic
+//                   (mb_core.cuh) and writes forces / new state straight to HBM with
+//                   coalesced stores.  Per-muscle partial sums stay in registers across the
+//                   segment's column tiles and are reduced once per work item (warp
+//                   shuffles + one shared-memory stage, named barrier over the consumers).
+//
+// Bulk copies need 16-byte aligned global addresses: rows are 8-byte elements, so the
+// kernel requires an even row length L and starts each row copy at the even element at or
+// below the tile start (`shift` = 0 or 1, identical for all rows because L is even).
+// Layouts that do not qualify (odd L) and the stage / per-unit-input / mask variants use
+// the generic k1_step kernel instead.
+#pragma once
+
+namespace mb {
+
+constexpr int kStreamRows = 8;          // R: rows advanced together by a block
+
+template <typename T> struct StreamTraits;
+template <> struct StreamTraits<float>  { using U = UnitF; using P = float4;  using S = ScalF; };
+template <> struct StreamTraits<double> { using U = UnitD; using P = double2; using S = ScalD; };
+
+template <typename T>
+struct K1sArgs {
+    const typename StreamTraits<T>::P* params;
+    int64_t rows, L;
+    int32_t S, W, NS;
+    const int32_t* seg_off;
+    const double* seg_div;
+    int32_t peripheral;
+    const T* in;                 // [rows, S]
+    double* cpf;
+    double* dur;
+    T* forces;                   // may be NULL
+    T* totals;                   // may be NULL
+    double dt, adk_d, max_dur;
+    typename StreamTraits<T>::S sc;
+};
+
+// one unit, one step; state in, state out (no memory access)
+template <bool CENTRAL, bool RECOVERY>
+__device__ __forceinline__ float k1s_unit(const K1sArgs<float>& a, const UnitF& p, float x, double c, double d,
+                                          double fatdt, double rdidt, double ptf, double& cn, double& dn) {
+    bool on;
+    float r = pool_rate_raw(p, a.sc, x, on);
+    r = on ? r : 0.0f;                                                  // pool:171-172
+    float fr = r;
+    if (CENTRAL) {
+        fr = r - fmaxf(pool_adaptation(p, r, (float)(d * a.adk_d)), 0.0f);   // pool:221, :121
+        dn = duration_update(d, r > 0.0f, a.dt, a.max_dur);
+    }
+    float nf;
+    const float F = fibers_force(p, a.sc, fr, (float)c, nf);
+    cn = fatigue_update<RECOVERY>(c, (double)nf, fatdt, rdidt, ptf);
+    return F;
+}
+template <bool CENTRAL, bool RECOVERY>
+__device__ __forceinline__ double k1s_unit(const K1sArgs<double>& a, const UnitD& p, double x, double c, double d,
+                                           double fatdt, double rdidt, double ptf, double& cn, double& dn) {
+    bool on;
+    const double r = pool_rate(p, a.sc, x, on);
+    double fr = r;
+    if (CENTRAL) {
+        fr = pool_adapt(p, a.sc, r, d);
+        dn = duration_update(d, r > 0.0, a.dt, a.max_dur);
+    }
+    double nf;
+    const double F = fibers_force(p, a.sc, fr, c, nf);
+    cn = fatigue_update<RECOVERY>(c, nf, fatdt, rdidt, ptf);
+    return F;
+}
+__device__ __forceinline__ double unit_ptf(const UnitF& p) { return (double)p.ptf + (double)p.ptf_lo; }
+__device__ __forceinline__ double unit_ptf(const UnitD& p) { return p.ptf; }
+
+template <typename T, bool CENTRAL, bool RECOVERY, bool FORCES>
+__global__ void __launch_bounds__(288, 2) k1_stream(const K1sArgs<T> a) {
+    constexpr int R = kStreamRows;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int W = a.W, NS = a.NS;
+    const int rowp = W + 2;                               // stage row pitch in elements (shift + round-up slack)
+    const uint32_t bar0 = smem_u32(smem_raw);             // full[NS] | empty[NS]
+    double* cpf_s = (double*)(smem_raw + 128);            // [NS][R][rowp]
+    double* dur_s = cpf_s + (size_t)NS * R * rowp;        // [NS][R][rowp]   (CENTRAL only)
+    T* red = (T*)(CENTRAL ? dur_s + (size_t)NS * R * rowp : dur_s);   // [R][8]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ncons = blockDim.x - 32;                    // consumer threads (== W)
+    const int ncw = ncons >> 5;
+    if (tid == 0) {
+        for (int i = 0; i < NS; ++i) {
+            mbar_init(bar0 + 8u * i, 1);                  // full: the producer's expect_tx arrival
+            mbar_init(bar0 + 8u * (NS + i), ncw);         // empty: one arrival per consumer warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int64_t chunks = (a.rows + R - 1) / R;
+    const int64_t items = chunks * a.S;
+
+    if (warp == ncw) {
+        // ------------------------------ producer warp ----------------------------------------
+        uint32_t it = 0;
+        for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+            const int64_t chunk = item / a.S;
+            const int seg = (int)(item - chunk * a.S);
+            const int64_t r0 = chunk * R;
+            const int off0 = a.seg_off ? a.seg_off[seg] : 0;
+            const int n = a.seg_off ? a.seg_off[seg + 1] - off0 : (int)a.L;
+            const int nrows = (int)min((int64_t)R, a.rows - r0);
+            for (int u0 = 0; u0 < n; u0 += W, ++it) {
+                const uint32_t s = it % NS, ph = (it / NS) & 1;
+                mbar_wait(bar0 + 8u * (NS + s), ph ^ 1);  // stage free (passes at once in the first round)
+                const int count = min(W, n - u0);
+                const int64_t e0 = off0 + u0;             // element offset inside a row
+                const int64_t a0 = e0 & ~(int64_t)1, a1 = (e0 + count + 1) & ~(int64_t)1;
+                const uint32_t bytes = (uint32_t)(a1 - a0) * 8u;
+                if (lane == 0) mbar_expect_tx(bar0 + 8u * s, bytes * nrows * (CENTRAL ? 2u : 1u));
+                __syncwarp();
+                if (lane < nrows) {
+                    const int64_t g = (r0 + lane) * a.L + a0;
+                    const uint32_t so = (uint32_t)((s * R + lane) * rowp) * 8u;
+                    bulk_g2s(smem_u32(cpf_s) + so, a.cpf + g, bytes, bar0 + 8u * s);
+                    if (CENTRAL) bulk_g2s(smem_u32(dur_s) + so, a.dur + g, bytes, bar0 + 8u * s);
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------- consumer warps ----------------------------------------
+    // the per-muscle inputs of the NEXT work item are fetched while the current one is processed
+    auto fetch_inputs = [&](int64_t item, T (&x)[R]) {
+        const int64_t chunk = item / a.S;
+        const int seg = (int)(item - chunk * a.S);
+        const int64_t r0 = chunk * R;
+#pragma unroll
+        for (int r = 0; r < R; ++r) x[r] = (item < items && r0 + r < a.rows) ? a.in[(r0 + r) * a.S + seg] : T(0);
+    };
+    uint32_t it = 0;
+    T xnext[R];
+    fetch_inputs(blockIdx.x, xnext);
+    for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+        const int64_t chunk = item / a.S;
+        const int seg = (int)(item - chunk * a.S);
+        const int64_t r0 = chunk * R;
+        const int off0 = a.seg_off ? a.seg_off[seg] : 0;
+        const int n = a.seg_off ? a.seg_off[seg + 1] - off0 : (int)a.L;
+        const int nrows = (int)min((int64_t)R, a.rows - r0);
+        T xm[R], partial[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            partial[r] = 0;
+            xm[r] = xnext[r];
+        }
+        fetch_inputs(item + gridDim.x, xnext);
+        for (int u0 = 0; u0 < n; u0 += W, ++it) {
+            const uint32_t s = it % NS, ph = (it / NS) & 1;
+            const int u = u0 + tid;
+            const bool active = u < n;
+            const auto p = load_unit(a.params, a.L, off0 + (active ? u : 0));
+            const double fatdt = (double)p.fat * a.dt, rdidt = (double)p.rdi * a.dt;
+            const double ptf = unit_ptf(p);
+            const int shift = (off0 + u0) & 1;
+            mbar_wait(bar0 + 8u * s, ph);
+            if (active) {
+                const double* cs = cpf_s + (s * R) * rowp + shift + tid;
+                const double* ds = dur_s + (s * R) * rowp + shift + tid;
+                double c[R], d[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    c[r] = cs[r * rowp];
+                    d[r] = CENTRAL ? ds[r * rowp] : 0.0;
+                }
+                const int64_t i0 = r0 * a.L + off0 + u;
+                T* fp = FORCES ? a.forces + i0 : nullptr;
+                double* cp = a.cpf + i0;
+                double* dp = CENTRAL ? a.dur + i0 : nullptr;
+                auto row = [&](int r) {
+                    double cn, dn = d[r];
+                    const T F = k1s_unit<CENTRAL, RECOVERY>(a, p, xm[r], c[r], d[r], fatdt, rdidt, ptf, cn, dn);
+                    if (FORCES) *fp = F;
+                    *cp = cn;
+                    if (CENTRAL) *dp = dn;
+                    partial[r] += F;
+                    if (FORCES) fp += a.L;
+                    cp += a.L;
+                    if (CENTRAL) dp += a.L;
+                };
+                if (nrows == R) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) row(r);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+                        if (r < nrows) row(r);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar0 + 8u * (NS + s));    // this warp is done with the stage
+        }
+        if (a.totals) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const T w = warp_sum(partial[r]);
+                if (lane == 0) red[r * 8 + warp] = w;
+            }
+            asm volatile("bar.sync 1, %0;" ::"r"(ncons) : "memory");
+            if (tid < nrows) {
+                T sum = red[tid * 8];
+                for (int w = 1; w < ncw; ++w) sum += red[tid * 8 + w];
+                a.totals[(r0 + tid) * a.S + seg] = a.seg_div ? out_div(sum, a.seg_div[seg]) : out_scale(a.sc, sum);
+            }
+            asm volatile("bar.sync 1, %0;" ::"r"(ncons) : "memory");
+        }
+    }
+}
+
+}  // namespace mb

@@ -192,60 +192,66 @@ struct K1Args {
     typename Vec<T>::S sc;
 };
 
-// per-unit work, FP32 mode: float arithmetic, float64 state
-__device__ __forceinline__ float k1_unit(const K1Args<float>& a, const UnitF& p, int64_t i, float x) {
+// Per-unit arithmetic of one step.  Loads and stores are done by the caller (all loads of a
+// thread's R rows are issued before any arithmetic so that they overlap); this only maps
+// (input x, capacity c, duration d) -> (force, new capacity, new duration, mask, rate).
+struct K1Out {
+    double c_new, d_new;
+    bool on;
+};
+
+// FP32 mode: float arithmetic, float64 state
+__device__ __forceinline__ float k1_compute(const K1Args<float>& a, const UnitF& p, float x, double c, double d,
+                                            K1Out& o, float& rate) {
     float fr = x;
+    o.on = false;
+    o.d_new = d;
+    o.c_new = c;
     if (a.stage != MB_STAGE_FIBERS) {
-        bool on;
-        float r = pool_rate_raw(p, a.sc, x, on);
-        r = on ? r : 0.0f;                                              // pool:171-172
+        float r = pool_rate_raw(p, a.sc, x, o.on);
+        r = o.on ? r : 0.0f;                                            // pool:171-172
         fr = r;
         if (a.central) {
-            const double d = a.dur[i];
             fr = r - fmaxf(pool_adaptation(p, r, (float)(d * a.adk_d)), 0.0f);   // pool:221, :121
-            a.dur[i] = duration_update(d, r > 0.0f, a.dt, a.max_dur);
+            o.d_new = duration_update(d, r > 0.0f, a.dt, a.max_dur);
         }
-        if (a.mask) a.mask[i] = on ? 1 : 0;
-        if (a.rates) a.rates[i] = fr;
+        rate = fr;
         if (a.stage == MB_STAGE_POOL) return 0.0f;
     }
-    const double c = a.cpf[i];
     float nf;
     const float F = fibers_force(p, a.sc, fr, (float)c, nf);
-    if (a.forces) a.forces[i] = F;
     if (a.peripheral) {
         const double fatdt = (double)p.fat * a.dt, rdidt = (double)p.rdi * a.dt;
         const double ptf = (double)p.ptf + (double)p.ptf_lo;
-        a.cpf[i] = a.recovery ? fatigue_update<true>(c, (double)nf, fatdt, rdidt, ptf)
-                              : fatigue_update<false>(c, (double)nf, fatdt, rdidt, ptf);
+        o.c_new = a.recovery ? fatigue_update<true>(c, (double)nf, fatdt, rdidt, ptf)
+                             : fatigue_update<false>(c, (double)nf, fatdt, rdidt, ptf);
     }
     return F;
 }
 
-// per-unit work, FP64 mode
-__device__ __forceinline__ double k1_unit(const K1Args<double>& a, const UnitD& p, int64_t i, double x) {
+// FP64 mode
+__device__ __forceinline__ double k1_compute(const K1Args<double>& a, const UnitD& p, double x, double c, double d,
+                                             K1Out& o, double& rate) {
     double fr = x;
+    o.on = false;
+    o.d_new = d;
+    o.c_new = c;
     if (a.stage != MB_STAGE_FIBERS) {
-        bool on;
-        const double r = pool_rate(p, a.sc, x, on);
+        const double r = pool_rate(p, a.sc, x, o.on);
         fr = r;
         if (a.central) {
-            const double d = a.dur[i];
             fr = pool_adapt(p, a.sc, r, d);
-            a.dur[i] = duration_update(d, r > 0.0, a.dt, a.max_dur);
+            o.d_new = duration_update(d, r > 0.0, a.dt, a.max_dur);
         }
-        if (a.mask) a.mask[i] = on ? 1 : 0;
-        if (a.rates) a.rates[i] = fr;
+        rate = fr;
         if (a.stage == MB_STAGE_POOL) return 0.0;
     }
-    const double c = a.cpf[i];
     double nf;
     const double F = fibers_force(p, a.sc, fr, c, nf);
-    if (a.forces) a.forces[i] = F;
     if (a.peripheral) {
         const double fatdt = p.fat * a.dt, rdidt = p.rdi * a.dt;
-        a.cpf[i] = a.recovery ? fatigue_update<true>(c, nf, fatdt, rdidt, p.ptf)
-                              : fatigue_update<false>(c, nf, fatdt, rdidt, p.ptf);
+        o.c_new = a.recovery ? fatigue_update<true>(c, nf, fatdt, rdidt, p.ptf)
+                             : fatigue_update<false>(c, nf, fatdt, rdidt, p.ptf);
     }
     return F;
 }
@@ -255,39 +261,75 @@ __device__ __forceinline__ double out_scale(const ScalD& s, double v) { return v
 __device__ __forceinline__ float  out_div(float v, double d)  { return (float)((double)v / d); }
 __device__ __forceinline__ double out_div(double v, double d) { return v / d; }
 
-template <typename T>
-__global__ void __launch_bounds__(256) k1_step(const K1Args<T> a) {
-    __shared__ T red[8][8];                       // [ty][warp within the muscle's TX threads]
-    const int tx = threadIdx.x, ty = threadIdx.y, TX = blockDim.x, TY = blockDim.y;
-    const int warp_in_row = tx >> 5, warps_per_row = TX >> 5;
-    const int64_t n_muscles = a.rows * a.S;
-    for (int64_t base = (int64_t)blockIdx.x * TY; base < n_muscles; base += (int64_t)gridDim.x * TY) {
-        const int64_t mu = base + ty;
-        const bool valid = mu < n_muscles;
-        T partial = 0;
-        if (valid) {
-            const int64_t row = mu / a.S;
-            const int seg = (int)(mu - row * a.S);
-            const int off0 = a.seg_off ? a.seg_off[seg] : 0;
-            const int n = a.seg_off ? a.seg_off[seg + 1] - off0 : (int)a.L;
-            const int64_t ubase = row * a.L + off0;
-            const T xm = a.in_per_unit ? T(0) : a.in[mu];
-            for (int u = tx; u < n; u += TX) {
-                const auto p = load_unit(a.params, a.L, off0 + u);
-                const int64_t i = ubase + u;
-                const T x = a.in_per_unit ? a.in[i] : xm;
-                partial += k1_unit(a, p, i, x);
+// One block = one muscle (segment) of R consecutive rows at a time.  A thread owns unit
+// positions tx, tx+TX, ... of the segment and advances that unit in all R rows: the unit's
+// parameters (48 / 80 bytes from L2) are loaded once per R unit-steps, so L2 traffic stays
+// below the HBM traffic of the state (20-40 bytes per unit-step), and the R rows give R
+// independent HBM loads in flight per thread.
+template <typename T, int R, int MINB>
+__global__ void __launch_bounds__(256, MINB) k1_step(const K1Args<T> a) {
+    __shared__ T red[R][8];
+    const int tx = threadIdx.x, TX = blockDim.x, lane = tx & 31, warp = tx >> 5, nwarps = TX >> 5;
+    const int64_t chunks = (a.rows + R - 1) / R;
+    const int64_t items = chunks * a.S;
+    const bool need_c = a.stage != MB_STAGE_POOL;
+    const bool need_d = a.stage != MB_STAGE_FIBERS && a.central;
+    for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+        const int64_t chunk = item / a.S;
+        const int seg = (int)(item - chunk * a.S);
+        const int64_t r0 = chunk * R;
+        const int off0 = a.seg_off ? a.seg_off[seg] : 0;
+        const int n = a.seg_off ? a.seg_off[seg + 1] - off0 : (int)a.L;
+        const int nrows = (int)min((int64_t)R, a.rows - r0);
+        T xm[R], partial[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            partial[r] = 0;
+            xm[r] = (!a.in_per_unit && r < nrows) ? a.in[(r0 + r) * a.S + seg] : T(0);
+        }
+        for (int u = tx; u < n; u += TX) {
+            const auto p = load_unit(a.params, a.L, off0 + u);
+            const int64_t i0 = r0 * a.L + off0 + u;
+            double c[R], d[R];
+            T x[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {                    // all loads first
+                const int64_t i = i0 + (int64_t)r * a.L;
+                const bool v = r < nrows;
+                c[r] = (v && need_c) ? a.cpf[i] : 0.0;
+                d[r] = (v && need_d) ? a.dur[i] : 0.0;
+                x[r] = a.in_per_unit ? (v ? a.in[i] : T(0)) : xm[r];
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (r >= nrows) continue;
+                const int64_t i = i0 + (int64_t)r * a.L;
+                K1Out o;
+                T rate = 0;
+                const T F = k1_compute(a, p, x[r], c[r], d[r], o, rate);
+                if (need_d) a.dur[i] = o.d_new;
+                if (a.stage != MB_STAGE_FIBERS) {
+                    if (a.mask) a.mask[i] = o.on ? 1 : 0;
+                    if (a.rates) a.rates[i] = rate;
+                }
+                if (need_c) {
+                    if (a.forces) a.forces[i] = F;
+                    if (a.peripheral) a.cpf[i] = o.c_new;
+                    partial[r] += F;
+                }
             }
         }
-        if (a.totals && a.stage != MB_STAGE_POOL) {          // block-uniform condition
-            partial = warp_sum(partial);
-            if ((tx & 31) == 0) red[ty][warp_in_row] = partial;
+        if (a.totals && need_c) {                             // block-uniform condition
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const T w = warp_sum(partial[r]);
+                if (lane == 0) red[r][warp] = w;
+            }
             __syncthreads();
-            if (tx == 0 && valid) {
-                T s = red[ty][0];
-                for (int w = 1; w < warps_per_row; ++w) s += red[ty][w];
-                const int seg = (int)(mu % a.S);
-                a.totals[mu] = a.seg_div ? out_div(s, a.seg_div[seg]) : out_scale(a.sc, s);
+            if (tx < nrows) {
+                T s = red[tx][0];
+                for (int w = 1; w < nwarps; ++w) s += red[tx][w];
+                a.totals[(r0 + tx) * a.S + seg] = a.seg_div ? out_div(s, a.seg_div[seg]) : out_scale(a.sc, s);
             }
             __syncthreads();
         }
@@ -295,6 +337,7 @@ __global__ void __launch_bounds__(256) k1_step(const K1Args<T> a) {
 }
 
 #include "mb_fused.cuh"
+#include "mb_stream.cuh"
 
 // =====================================================================================
 // K3: per-muscle capacity sums (StandardMuscle.get_peripheral_fatigue, muscle.py:248-256)
@@ -460,6 +503,11 @@ extern "C" int mb_peak_probe(int32_t kind, int32_t blocks, int32_t threads, int3
 // =====================================================================================
 // launchers
 // =====================================================================================
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
 static int sm_count() {
     static int n = 0;
     if (n == 0) {
@@ -488,21 +536,93 @@ static int launch_k1(const MbConfig& c, const void* params, int64_t rows, int64_
     a.adk_d = -kLog2e / c.adaptation_time_constant;
     a.max_dur = c.max_duration;
     a.sc = sc;
-    // threads per muscle: enough for the mean segment, at most 256; rows of the block = other muscles
+    // threads per block: enough for the mean segment (a multiple of 32, at most 256)
     const int64_t mean_n = (L + S - 1) / S;
     int tx = (int)((mean_n + 31) / 32) * 32;
     if (tx > 256) tx = 256;
     if (tx < 32) tx = 32;
-    int ty = 256 / tx;
-    if (ty > 8) ty = 8;
-    const int64_t n_muscles = rows * S;
-    int64_t blocks = (n_muscles + ty - 1) / ty;
-    const int64_t cap = (int64_t)sm_count() * 16;
+    const int R = env_int("MB_K1_R", 8);                      // rows advanced together by a block
+    const int64_t items = ((rows + R - 1) / R) * S;
+    int64_t blocks = items;
+    const int64_t cap = (int64_t)sm_count() * (2048 / tx) * 4;   // a few waves of resident blocks
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    k1_step<T><<<(unsigned)blocks, dim3(tx, ty), 0, st>>>(a);
+    const int minb = env_int("MB_K1_MINB", 3);
+    if (R == 4) {
+        if (minb >= 4) k1_step<T, 4, 4><<<(unsigned)blocks, tx, 0, st>>>(a);
+        else k1_step<T, 4, 2><<<(unsigned)blocks, tx, 0, st>>>(a);
+    } else {
+        if (minb >= 4) k1_step<T, 8, 4><<<(unsigned)blocks, tx, 0, st>>>(a);
+        else if (minb == 3) k1_step<T, 8, 3><<<(unsigned)blocks, tx, 0, st>>>(a);
+        else k1_step<T, 8, 2><<<(unsigned)blocks, tx, 0, st>>>(a);
+    }
     MB_CUDA_OK(cudaGetLastError());
     return MB_OK;
+}
+
+// ---- K1s launcher ---------------------------------------------------------------------------
+template <typename T, bool CENTRAL, bool RECOVERY, bool FORCES>
+static int launch_k1s_variant(const K1sArgs<T>& a, int threads, int smem, int64_t items, cudaStream_t st) {
+    auto kern = k1_stream<T, CENTRAL, RECOVERY, FORCES>;
+    if (smem > 48 * 1024) MB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    // persistent grid: exactly the blocks that are resident at once, each walking the work list
+    int per_sm = 0;
+    MB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+    if (per_sm < 1) return fail(MB_ECUDA, "k1_stream does not fit on an SM (threads %d, smem %d)", threads, smem);
+    const int cap = env_int("MB_K1_BPS", 0);
+    if (cap > 0 && per_sm > cap) per_sm = cap;
+    int64_t blocks = (int64_t)sm_count() * per_sm;
+    if (blocks > items) blocks = items;
+    kern<<<(unsigned)blocks, threads, smem, st>>>(a);
+    MB_CUDA_OK(cudaGetLastError());
+    return MB_OK;
+}
+
+// The streaming kernel covers the batched hot case: whole-muscle stage, one input per muscle,
+// no mask / rate outputs, even row length, 16-byte aligned state arrays.
+template <typename T>
+static bool k1s_eligible(const MbConfig& c, int64_t L, int32_t stage, int32_t in_per_unit, const double* cpf,
+                         const double* dur, const uint8_t* mask, const void* rates) {
+    if (env_int("MB_K1_GENERIC", 0)) return false;
+    if (stage != MB_STAGE_MUSCLE || in_per_unit || mask || rates || !c.peripheral_fatigue) return false;
+    if (L % 2 != 0 || ((uintptr_t)cpf % 16) != 0) return false;
+    if (c.central_fatigue && ((uintptr_t)dur % 16) != 0) return false;
+    return true;
+}
+
+template <typename T>
+static int launch_k1s(const MbConfig& c, const void* params, int64_t rows, int64_t L, int32_t S,
+                      const int32_t* seg_off, const double* seg_div, const void* in, double* cpf, double* dur,
+                      void* forces, void* totals, double dt, cudaStream_t st, const typename Vec<T>::S& sc) {
+    K1sArgs<T> a;
+    a.params = (const typename StreamTraits<T>::P*)params;
+    a.rows = rows; a.L = L; a.S = S; a.seg_off = seg_off; a.seg_div = seg_div;
+    a.peripheral = c.peripheral_fatigue != 0;
+    a.in = (const T*)in; a.cpf = cpf; a.dur = dur; a.forces = (T*)forces; a.totals = (T*)totals;
+    a.dt = dt;
+    a.adk_d = -kLog2e / c.adaptation_time_constant;
+    a.max_dur = c.max_duration;
+    a.sc = sc;
+    const bool central = c.central_fatigue != 0, recovery = c.fibers_kind == MB_FIBERS_PYMUSCLE;
+    const int64_t mean_n = (L + S - 1) / S;
+    int W = (int)((mean_n + 31) / 32) * 32;
+    const int wmax = env_int("MB_K1_W", 256);
+    if (W > wmax) W = wmax;
+    if (W < 32) W = 32;
+    const int stage_bytes = kStreamRows * (W + 2) * 8 * (central ? 2 : 1);
+    int NS = env_int("MB_K1_STAGES", 0);
+    if (NS <= 0) NS = 3;                                      // measured: 3 stages x 2+ blocks/SM saturate HBM; deeper rings only cost occupancy
+    if (NS > 8) NS = 8;
+    if (NS < 2) NS = 2;
+    a.W = W; a.NS = NS;
+    const int threads = W + 32;
+    const int smem = 128 + NS * stage_bytes + kStreamRows * 8 * (int)sizeof(T);
+    const int64_t items = ((rows + kStreamRows - 1) / kStreamRows) * S;
+#define MB_K1S(C_, R_) (forces ? launch_k1s_variant<T, C_, R_, true>(a, threads, smem, items, st) \
+                               : launch_k1s_variant<T, C_, R_, false>(a, threads, smem, items, st))
+    if (central) return recovery ? MB_K1S(true, true) : MB_K1S(true, false);
+    return recovery ? MB_K1S(false, true) : MB_K1S(false, false);
+#undef MB_K1S
 }
 
 extern "C" int mb_step(const MbConfig* cfg, const void* params_dev, int64_t rows, int64_t L, int32_t S,
@@ -518,9 +638,16 @@ extern "C" int mb_step(const MbConfig* cfg, const void* params_dev, int64_t rows
     if (stage != MB_STAGE_FIBERS && cfg->central_fatigue && !dur_dev) return fail(MB_EINVAL, "mb_step: dur is NULL");
     if (stage == MB_STAGE_FIBERS && !in_per_unit) return fail(MB_EINVAL, "mb_step: firing rates must be per unit");
     cudaStream_t st = (cudaStream_t)stream;
-    if (cfg->precision == MB_F32)
+    if (cfg->precision == MB_F32) {
+        if (k1s_eligible<float>(*cfg, L, stage, in_per_unit, cpf_dev, dur_dev, mask_dev, rates_dev))
+            return launch_k1s<float>(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, in_dev, cpf_dev, dur_dev,
+                                     forces_dev, totals_dev, step_size, st, scal_f(*cfg));
         return launch_k1<float>(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, stage, in_dev, in_per_unit, cpf_dev,
                                 dur_dev, forces_dev, totals_dev, mask_dev, rates_dev, step_size, st, scal_f(*cfg));
+    }
+    if (k1s_eligible<double>(*cfg, L, stage, in_per_unit, cpf_dev, dur_dev, mask_dev, rates_dev))
+        return launch_k1s<double>(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, in_dev, cpf_dev, dur_dev,
+                                  forces_dev, totals_dev, step_size, st, scal_d(*cfg));
     return launch_k1<double>(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, stage, in_dev, in_per_unit, cpf_dev, dur_dev,
                              forces_dev, totals_dev, mask_dev, rates_dev, step_size, st, scal_d(*cfg));
 }
@@ -546,10 +673,6 @@ struct FusedGeom {
     int64_t blocks;
 };
 
-static int env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return (v && *v) ? atoi(v) : dflt;
-}
 
 static const int kFusedMaxUnits = 480;     // threads per block <= 480 (15 warps), 2 blocks per SM in FP32 mode
 
