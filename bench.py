@@ -184,6 +184,16 @@ BAD_REASONS = {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
 # ======================================================================================
 # GPU arm
 # ======================================================================================
+def ncu_traffic(kernel_key):
+    """DRAM bytes per launch of a kernel from the committed ncu --set full capture
+    (profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(kernel_key)
+    except Exception:
+        return None
+
+
 def measured_hbm_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -251,9 +261,10 @@ def run_gpu_arm(args):
     peak_lane_ops = probe(probe_kind, 4096 if probe_kind == 0 else 1024)
 
     # ---- timed region ------------------------------------------------------------------------
-    def timed(fn, steps, warmup, counter=lambda: 0):
+    def timed(fn, steps, warmup, counter=lambda: 0, join=lambda: None):
         for _ in range(warmup):
             fn()
+        join()
         torch.cuda.synchronize()
         barrier()
         sampler = ClockSampler(local_rank)
@@ -263,6 +274,7 @@ def run_gpu_arm(args):
         a.record()
         for _ in range(steps):
             fn()
+        join()                                                # side streams (downloads) rejoin the timed stream
         b.record()
         torch.cuda.synchronize()
         barrier()
@@ -293,14 +305,16 @@ def run_gpu_arm(args):
         e_steps = max(3, min(args.steps, 20))
 
         def window_host():
-            batch.step_many_host(exc_h, dt, out_h, chunk=args.chunk)
+            batch.step_many_host(exc_h, dt, out_h, chunk=args.chunk, overlap_calls=True)
 
-        sec_e, _ = timed(window_host, e_steps, 3)
+        sec_e, _ = timed(window_host, e_steps, 3, join=batch.host_pipeline_join)
         e2e = {"value": world * unit_steps * e_steps / sec_e, "unit": METRIC,
                "h2d_bytes_per_step": exc_h.numel() * exc_h.element_size(),
                "d2h_bytes_per_step": out_h.numel() * out_h.element_size(),
                "steps": e_steps, "ms_per_step": 1e3 * sec_e / e_steps,
-               "api": f"MuscleBatch.step_many_host(pinned exc[{K},{M}], dt, pinned totals[{K},{M}], chunk={args.chunk})"}
+               "api": f"MuscleBatch.step_many_host(pinned exc[{K},{M}], dt, pinned totals[{K},{M}], chunk={args.chunk}, overlap_calls=True): "
+                      "H2D / fused kernel / D2H of sub-windows on three streams; every window's excitations are "
+                      "uploaded and its totals downloaded inside the timed region"}
         del exc_h, out_h
 
     # ---- the single-step kernel against the HBM roofline (BASELINE config #5 shape) -----------
@@ -321,9 +335,11 @@ def run_gpu_arm(args):
         sec5, _ = timed(frame, 50, 5)
         us5 = b5.n_units * 50 / sec5
         bytes_per = K1_BYTES_PER_UNIT_STEP["standard_f32"]
-        k1 = {"kernel": "k1_step<float>", "workload": f"StandardMuscle n=2000 x {m5}, one launch per frame",
+        k1 = {"kernel": "k1_stream<float>", "workload": f"StandardMuscle n=2000 x {m5}, one launch per frame",
               "bound": "hbm", "achieved": us5 * bytes_per / 1e9, "peak": hbm_peak, "unit": "GB/s",
-              "frac": us5 * bytes_per / 1e9 / hbm_peak, "peak_source": hbm_src, "traffic": None,
+              "frac": us5 * bytes_per / 1e9 / hbm_peak, "peak_source": hbm_src,
+              "traffic": ncu_traffic("k1_stream_f32_config5"),
+              "algorithmic_bytes_per_launch": b5.n_units * bytes_per,
               "bytes_per_unit_step": bytes_per, "value": us5, "value_unit": METRIC}
 
     if rank != 0:
@@ -342,12 +358,15 @@ def run_gpu_arm(args):
         "roofline": {
             "kernel": f"k2_fused_{args.precision}", "bound": pipe, "achieved": achieved,
             "peak": peak_lane_ops / 1e12, "unit": "Tlane-op/s", "frac": achieved / (peak_lane_ops / 1e12),
-            "traffic": None,
+            "traffic": ncu_traffic("k2_fused_f32_config2"),
             "ops_per_unit_step": ops,
             "peak_source": "mb_peak_probe dependent-FMA chains (8 per thread), best of 3, measured in this run; "
                            "MEASURED_PEAKS.json has no FP32/FP64 pipe figure",
-            "note": "achieved = 38 canonical FP operations (SURVEY.md A.2, FMA not used in the count, exp = 1) "
-                    "x unit-steps per launch / mean launch time; peak counts one lane-op per FMA instruction lane"},
+            "note": "achieved = 38 canonical FP operations per unit-step (SURVEY.md A.2 / 8d: the reference's own "
+                    "operation list, FMA not used in the count, exp = 1) x unit-steps per launch / mean launch time; "
+                    "peak = one lane-op per FFMA lane.  The kernel needs fewer issue slots than 38 per unit-step "
+                    "(FMA contraction, packed FFMA2/FMUL2/FADD2, exp(-dur/tau) by recurrence), so frac can exceed 1; "
+                    "profiles/ holds the ncu issue-slot and pipe utilisation of the same launch"},
         "roofline_single_step": k1,
         "cpu_baseline": cpu,
         "fused_geometry": batch.fused_geometry(K, args.units_per_thread),
@@ -368,7 +387,7 @@ def main():
     ap.add_argument("--muscles", type=int, default=65536)
     ap.add_argument("--window", type=int, default=1000)
     ap.add_argument("--units-per-thread", type=int, default=0)
-    ap.add_argument("--chunk", type=int, default=125, help="sub-window length of the host-buffer pipeline")
+    ap.add_argument("--chunk", type=int, default=104, help="sub-window length of the host-buffer pipeline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-k1", action="store_true")

@@ -226,7 +226,7 @@ class MuscleBatch:
 
     # ---- K2 with host buffers: H2D / compute / D2H pipelined over sub-windows ---------
     def step_many_host(self, exc_host: torch.Tensor, step_size: float, out_host: torch.Tensor,
-                       chunk: int = 125) -> torch.Tensor:
+                       chunk: int = 104, overlap_calls: bool = False) -> torch.Tensor:
         """``step_many`` for excitations and totals that live in (pinned) HOST memory.
 
         The window is cut into sub-windows of ``chunk`` steps; the host->device copy of
@@ -234,6 +234,13 @@ class MuscleBatch:
         sub-window i-1 run concurrently on three streams (double-buffered staging), so the
         call costs max(PCIe, kernel) rather than their sum.  Returns ``out_host``; the
         caller's current stream is made to wait for the last copy.
+
+        overlap_calls  False: the first upload waits for everything already queued on the current
+                       stream (safe if ``exc_host`` is being produced by stream work).  True: the
+                       upload only waits for the staging buffer to be free, so back-to-back calls
+                       overlap this window's first upload with the previous window's last download
+                       (``exc_host`` must already hold its final contents at call time, and the
+                       caller joins with ``host_pipeline_join()`` before reading ``out_host``).
         """
         K, M = int(exc_host.shape[0]), self.n_muscles
         assert exc_host.device.type == "cpu" and out_host.device.type == "cpu"
@@ -250,26 +257,36 @@ class MuscleBatch:
                           down=[torch.cuda.Event() for _ in range(2)])
             self._host_pipe = st
         cur = torch.cuda.current_stream(self.device)
-        st["h2d"].wait_stream(cur)
-        st["d2h"].wait_stream(cur)
+        if not overlap_calls:
+            st["h2d"].wait_stream(cur)
+        first = not st.get("used", False)
+        st["used"] = True
         for i, k0 in enumerate(range(0, K, chunk)):
             b, c = i & 1, min(chunk, K - k0)
-            if i >= 2:
-                st["h2d"].wait_event(st["run"][b])           # kernel i-2 has consumed exc[b]
+            if i >= 2 or not first:
+                st["h2d"].wait_event(st["run"][b])           # the last kernel that read exc[b] is done
             with torch.cuda.stream(st["h2d"]):
                 st["exc"][b][:c].copy_(exc_host[k0:k0 + c], non_blocking=True)
                 st["up"][b].record(st["h2d"])
             cur.wait_event(st["up"][b])
-            if i >= 2:
-                cur.wait_event(st["down"][b])                # copy-out i-2 has drained tot[b]
+            if i >= 2 or not first:
+                cur.wait_event(st["down"][b])                # the last copy-out of tot[b] has drained
             self.step_many(st["exc"][b][:c], step_size, out=st["tot"][b][:c])
             st["run"][b].record(cur)
             st["d2h"].wait_event(st["run"][b])
             with torch.cuda.stream(st["d2h"]):
                 out_host[k0:k0 + c].copy_(st["tot"][b][:c], non_blocking=True)
                 st["down"][b].record(st["d2h"])
-        cur.wait_stream(st["d2h"])
+        if not overlap_calls:
+            cur.wait_stream(st["d2h"])
         return out_host
+
+    def host_pipeline_join(self):
+        """Make the current stream wait for every download queued by ``step_many_host``
+        (needed after calls with ``overlap_calls=True`` before the results are consumed)."""
+        st = getattr(self, "_host_pipe", None)
+        if st is not None:
+            torch.cuda.current_stream(self.device).wait_stream(st["d2h"])
 
     # ---- observers --------------------------------------------------------------------
     @property
