@@ -261,12 +261,14 @@ def run_gpu_arm(args):
     peak_lane_ops = probe(probe_kind, 4096 if probe_kind == 0 else 1024)
 
     # ---- timed region ------------------------------------------------------------------------
-    def timed(fn, steps, warmup, counter=lambda: 0, join=lambda: None):
+    def timed(fn, steps, warmup, counter=lambda: 0, join=lambda: None, collective=True):
+        """`collective`: every rank runs this region (barriers + max over ranks); False = this rank only."""
+        sync = barrier if collective else (lambda: None)
         for _ in range(warmup):
             fn()
         join()
         torch.cuda.synchronize()
-        barrier()
+        sync()
         sampler = ClockSampler(local_rank)
         sampler.start()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -277,11 +279,11 @@ def run_gpu_arm(args):
         join()                                                # side streams (downloads) rejoin the timed stream
         b.record()
         torch.cuda.synchronize()
-        barrier()
+        sync()
         clocks = sampler.stop()
         clocks["launches"] = counter() - c0
         sec = a.elapsed_time(b) * 1e-3
-        if world > 1:
+        if world > 1 and collective:
             t = torch.tensor([sec], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             sec = float(t.item())
@@ -332,7 +334,7 @@ def run_gpu_arm(args):
             b5.step(x5[it[0] & 3], dt)
             it[0] += 1
 
-        sec5, _ = timed(frame, 50, 5)
+        sec5, _ = timed(frame, 50, 5, collective=False)     # rank 0 only: no barrier, no all-reduce
         us5 = b5.n_units * 50 / sec5
         bytes_per = K1_BYTES_PER_UNIT_STEP["standard_f32"]
         k1 = {"kernel": "k1_stream<float>", "workload": f"StandardMuscle n=2000 x {m5}, one launch per frame",
@@ -343,8 +345,8 @@ def run_gpu_arm(args):
               "bytes_per_unit_step": bytes_per, "value": us5, "value_unit": METRIC}
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        barrier()                                             # wait for rank 0's single-rank extras
+        dist.destroy_process_group()
         return 0
 
     ops = OPS_PER_UNIT_STEP["potvin"]
@@ -373,6 +375,7 @@ def run_gpu_arm(args):
     }
     print(json.dumps(line), flush=True)
     if world > 1:
+        barrier()
         dist.destroy_process_group()
     return 0
 
