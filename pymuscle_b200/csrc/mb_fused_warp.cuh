@@ -1,0 +1,147 @@
+// mb_fused_warp.cuh -- K2w: the fused K-step kernel for muscles of 33..128 units, FP32 mode.
+//
+// One WARP owns two consecutive muscles for the whole window and never talks to another
+// warp: lane l holds units l, l+32, l+64, l+96 (UPL = ceil(n/32) of them) of both muscles.
+// The two muscles of a unit form one packed pair (FFMA2 / FMUL2 / FADD2, CoreF32 with U = 2),
+// so a thread carries UPL independent pair chains with UPL parameter sets in registers.
+//
+// Per step a thread adds its UPL unit forces (packed adds) and stores one float2 into the
+// warp's private tile FTw[32][33] (shared memory).  Time is cut into tiles of 32 steps; after a
+// tile (one __syncwarp) lane s sums row s -- 32 bank-conflict-free 64-bit LDS -- and writes the
+// two muscles' totals of step k0+s.  There is no cross-warp reduction, no mbarrier and no
+// block barrier in the loop; warps drift freely.
+//
+// Excitations: lane s fetches the pair's two values of step k0+s of the NEXT tile while the
+// current tile is being computed (one load per lane per 32 steps), parks them in a private
+// shared-memory row, and every step is one broadcast LDS.64.
+//
+// exp(-dur/tau) - 1 is carried by recurrence and re-synchronised once per tile (CoreF32,
+// CENTRAL == 1); the compensated capacity pair is renormalised once per tile.
+#pragma once
+#include "mb_fused.cuh"
+
+namespace mb {
+
+constexpr int kWTile = 32;       // steps per tile: lanes of stage 1 = steps
+constexpr int kWPitch = 33;      // row pitch of FTw in float2 (odd => conflict free)
+constexpr int kWarpsPerBlock = 8;
+
+template <int FIB, int CENTRAL, int UPL, bool FORCES>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 2) k2w_f32(const K2Args a) {
+    using Core = CoreF32<FIB, CENTRAL, 2>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float2* ftw = (float2*)smem_raw + warp * (kWTile * kWPitch + 2 * kWTile);   // [32][33]
+    float2* excw = ftw + kWTile * kWPitch;                                       // [2][32]
+
+    const int n = a.n;
+    const int64_t m0 = ((int64_t)blockIdx.x * kWarpsPerBlock + warp) * 2;
+    if (m0 >= a.M) return;                                // warps are independent: no barrier below
+    const bool two = m0 + 1 < a.M;
+    const int ntiles = (a.K + kWTile - 1) / kWTile;
+    const float* exc = (const float*)a.exc;
+
+    Core core[UPL];
+#pragma unroll
+    for (int i = 0; i < UPL; ++i) {
+        const int u = lane + 32 * i;
+        const bool valid = u < n;
+        core[i].load(a, valid ? u : 0);
+        if (!valid) core[i].p.crit = __int_as_float(0x7f800000);        // idle slot: never recruited, force 0
+        if (valid) {
+            core[i].init(0, a, a.cpf[m0 * n + u], CENTRAL ? a.dur[m0 * n + u] : 0.0);
+            if (two) core[i].init(1, a, a.cpf[(m0 + 1) * n + u], CENTRAL ? a.dur[(m0 + 1) * n + u] : 0.0);
+        }
+    }
+
+    // excitations of (tile, step = lane) for the two muscles; 0 beyond the window / batch
+    auto fetch = [&](int tile) -> float2 {
+        float2 e = make_float2(0.0f, 0.0f);
+        const int k = tile * kWTile + lane;
+        if (k < a.K) {
+            const float* src = exc + (int64_t)k * a.exc_stride_k + m0;   // exc_stride_k == 0: constant
+            e.x = __ldg(src);
+            if (two) e.y = __ldg(src + 1);
+        }
+        return e;
+    };
+    float2 e_next = fetch(0);
+
+    for (int tile = 0; tile < ntiles; ++tile) {
+        const int k0 = tile * kWTile;
+        const int steps = min(kWTile, a.K - k0);
+        float2* es = excw + (tile & 1) * kWTile;
+        es[lane] = e_next;
+        __syncwarp();
+        if (tile + 1 < ntiles) e_next = fetch(tile + 1);
+#pragma unroll
+        for (int i = 0; i < UPL; ++i) core[i].begin_tile();
+
+        float2* fp = ftw + lane;
+        for (int s = 0; s < steps; ++s, fp += kWPitch) {
+            const float2 e = es[s];
+            float2 fsum;
+            bool write_now = false;
+            if (FORCES) write_now = ((k0 + s + 1) % a.forces_every) == 0;
+            const bool last = a.forces_last != nullptr && (k0 + s == a.K - 1);
+#pragma unroll
+            for (int i = 0; i < UPL; ++i) {
+                bool oa, ob;
+                const float2 F = core[i].step_pair(0, e, oa, ob);
+                fsum = (i == 0) ? F : __fadd2_rn(fsum, F);
+                {
+                    const int u = lane + 32 * i;
+                    if (u < n) {
+                        if (FORCES && write_now) {
+                            const int64_t base = (int64_t)((k0 + s) / a.forces_every) * a.M * n;
+                            float* fd = (float*)a.forces_dec;
+                            fd[base + m0 * n + u] = F.x;
+                            if (two) fd[base + (m0 + 1) * n + u] = F.y;
+                            if (a.mask_dec) {
+                                a.mask_dec[base + m0 * n + u] = oa ? 1 : 0;
+                                if (two) a.mask_dec[base + (m0 + 1) * n + u] = ob ? 1 : 0;
+                            }
+                        }
+                        if (last) {
+                            float* fl = (float*)a.forces_last;
+                            fl[m0 * n + u] = F.x;
+                            if (two) fl[(m0 + 1) * n + u] = F.y;
+                        }
+                    }
+                }
+            }
+            *fp = fsum;
+        }
+#pragma unroll
+        for (int i = 0; i < UPL; ++i) core[i].renormalise();
+        __syncwarp();
+        // ---- stage 1 (and only): lane s sums the 32 lanes' forces of step k0 + s -----------------
+        if (lane < steps) {
+            const float2* rp = ftw + lane * kWPitch;
+            float2 acc0 = rp[0], acc1 = rp[1];
+#pragma unroll
+            for (int c = 2; c < 32; c += 2) {
+                acc0 = __fadd2_rn(acc0, rp[c]);
+                acc1 = __fadd2_rn(acc1, rp[c + 1]);
+            }
+            const float2 acc = __fadd2_rn(acc0, acc1);
+            if (a.totals) {
+                float* t = (float*)a.totals + (int64_t)(k0 + lane) * a.totals_stride_k + m0;
+                t[0] = core[0].out_scale(acc.x);
+                if (two) t[1] = core[0].out_scale(acc.y);
+            }
+        }
+        __syncwarp();
+    }
+
+#pragma unroll
+    for (int i = 0; i < UPL; ++i) {
+        const int u = lane + 32 * i;
+        if (u < n) {
+            core[i].store(0, a, m0 * n + u);
+            if (two) core[i].store(1, a, (m0 + 1) * n + u);
+        }
+    }
+}
+
+}  // namespace mb

@@ -337,6 +337,7 @@ __global__ void __launch_bounds__(256, MINB) k1_step(const K1Args<T> a) {
 }
 
 #include "mb_fused.cuh"
+#include "mb_fused_warp.cuh"
 #include "mb_stream.cuh"
 
 // =====================================================================================
@@ -671,6 +672,7 @@ extern "C" int mb_peripheral_fatigue(const MbConfig* cfg, int64_t rows, int64_t 
 struct FusedGeom {
     int U, q, G, Gp, T, ns, npg, ptp, threads, smem;
     int64_t blocks;
+    int warp_kernel;      // 1: k2w_f32 (one warp per muscle pair), 0: k2_fused_* (block per muscle groups)
 };
 
 
@@ -682,6 +684,17 @@ static int fused_geometry(const MbConfig& c, int64_t M, int32_t n, int32_t K, in
     if (M <= 0 || K <= 0) return fail(MB_EINVAL, "M and K must be positive");
     const bool f32 = c.precision == MB_F32;
     const int esz = f32 ? 4 : 8;
+    g->warp_kernel = 0;
+    if (f32 && upt == 0 && n > 32 && n <= 128 && !env_int("MB_FUSED_BLOCK", 0)) {
+        // FP32 mode, 33..128 units: one warp per pair of muscles, no cross-warp reduction
+        g->warp_kernel = 1;
+        g->U = 2; g->q = kWarpsPerBlock; g->G = 2 * kWarpsPerBlock; g->Gp = g->G; g->T = kWTile;
+        g->ns = n; g->npg = 0; g->ptp = 0;
+        g->threads = kWarpsPerBlock * 32;
+        g->smem = kWarpsPerBlock * (kWTile * kWPitch + 2 * kWTile) * (int)sizeof(float2);
+        g->blocks = (M + g->G - 1) / g->G;
+        return MB_OK;
+    }
     const int ns = (n + 7) / 8 * 8;                          // threads per muscle group (stage-1 parts are 8 wide)
     int q = kFusedMaxUnits / ns;
     if (upt != 0 && upt != 1 && upt != 2 && upt != 4) return fail(MB_EINVAL, "units_per_thread must be 0, 1, 2 or 4");
@@ -799,6 +812,17 @@ extern "C" int mb_step_fused(const MbConfig* cfg, const void* params_dev, int64_
     const int fib = cfg->fibers_kind;
     const bool forces = forces_every > 0;
     cudaStream_t st = (cudaStream_t)stream;
+    if (g.warp_kernel) {
+        const int upl = (n + 31) / 32;
+#define MB_W_FORCES(FIB, CEN, UPL_)                                                             \
+    (forces ? launch_fused(k2w_f32<FIB, CEN, UPL_, true>, a, g, st) : launch_fused(k2w_f32<FIB, CEN, UPL_, false>, a, g, st))
+#define MB_W_UPL(FIB, CEN) (upl == 4 ? MB_W_FORCES(FIB, CEN, 4) : (upl == 3 ? MB_W_FORCES(FIB, CEN, 3) : MB_W_FORCES(FIB, CEN, 2)))
+#define MB_W_CEN(FIB) (cen == 0 ? MB_W_UPL(FIB, 0) : (cen == 1 ? MB_W_UPL(FIB, 1) : MB_W_UPL(FIB, 2)))
+        return fib == MB_FIBERS_POTVIN ? MB_W_CEN(MB_FIBERS_POTVIN) : MB_W_CEN(MB_FIBERS_PYMUSCLE);
+#undef MB_W_CEN
+#undef MB_W_UPL
+#undef MB_W_FORCES
+    }
     if (f32) {
         if (g.U == 4) return MB_DISPATCH_FIB(k2_fused_f32, 4);
         if (g.U == 2) return MB_DISPATCH_FIB(k2_fused_f32, 2);
