@@ -19,6 +19,7 @@
 // CENTRAL == 1); the compensated capacity pair is renormalised once per tile.
 #pragma once
 #include "mb_fused.cuh"
+#include <type_traits>
 
 namespace mb {
 
@@ -77,19 +78,19 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 2) k2w_f32(const K2Args a
 #pragma unroll
         for (int i = 0; i < UPL; ++i) core[i].begin_tile();
 
-        float2* fp = ftw + lane;
-        for (int s = 0; s < steps; ++s, fp += kWPitch) {
+        // one step of the warp's two muscles; LAST = the window's final step (current_forces wanted)
+        auto do_step = [&](int s, auto last_tag) {
+            constexpr bool LAST = decltype(last_tag)::value;
             const float2 e = es[s];
             float2 fsum;
             bool write_now = false;
             if (FORCES) write_now = ((k0 + s + 1) % a.forces_every) == 0;
-            const bool last = a.forces_last != nullptr && (k0 + s == a.K - 1);
 #pragma unroll
             for (int i = 0; i < UPL; ++i) {
                 bool oa, ob;
                 const float2 F = core[i].step_pair(0, e, oa, ob);
                 fsum = (i == 0) ? F : __fadd2_rn(fsum, F);
-                {
+                if (FORCES || LAST) {
                     const int u = lane + 32 * i;
                     if (u < n) {
                         if (FORCES && write_now) {
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 2) k2w_f32(const K2Args a
                                 if (two) a.mask_dec[base + (m0 + 1) * n + u] = ob ? 1 : 0;
                             }
                         }
-                        if (last) {
+                        if (LAST) {
                             float* fl = (float*)a.forces_last;
                             fl[m0 * n + u] = F.x;
                             if (two) fl[(m0 + 1) * n + u] = F.y;
@@ -110,8 +111,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 2) k2w_f32(const K2Args a
                     }
                 }
             }
-            *fp = fsum;
-        }
+            ftw[s * kWPitch + lane] = fsum;
+        };
+        const bool has_last = a.forces_last != nullptr && tile == ntiles - 1;
+        const int fast_steps = has_last ? steps - 1 : steps;
+        for (int s = 0; s < fast_steps; ++s) do_step(s, std::false_type{});
+        if (has_last) do_step(steps - 1, std::true_type{});
 #pragma unroll
         for (int i = 0; i < UPL; ++i) core[i].renormalise();
         __syncwarp();
