@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libmuscle_b200.so")
+LIB_PATH = os.environ.get("MB_LIB") or os.path.join(_HERE, "csrc", "libmuscle_b200.so")   # MB_LIB: tuning builds
 
 ABI_VERSION = 1
 

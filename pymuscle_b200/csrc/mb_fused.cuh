@@ -174,38 +174,49 @@ struct CoreF32 {
         }
     }
 
-    // one step of the pair pi; x = the two excitations; returns the two unit forces
+    // one step of the pair pi; x = the two excitations; returns the two unit forces.
+    // Recruitment enters the arithmetic as a float mask onf (1 = recruited): the firing rate is
+    // multiplied by it and the counter / adaptation recurrences are blended with it, so the FMA-pipe
+    // work stays packed and the only scalar (ALU-pipe) instructions are the two compares, the peak
+    // clamp, the curve select and the capacity clamp.
     __device__ __forceinline__ float2 step_pair(int pi, float2 x, bool& on_a, bool& on_b) {
         // ---- pool: rate and recruitment (pool:150-179) ----
         float2 r = __ffma2_rn(x, bc(sc.gain_e), bc(-p.thr_g));
-        on_a = x.x >= p.crit;
-        on_b = x.y >= p.crit;
+        float2 onf;
+        onf.x = (x.x >= p.crit) ? 1.0f : 0.0f;                              // pool:171 (exact mask: see mb_params_pack)
+        onf.y = (x.y >= p.crit) ? 1.0f : 0.0f;
         r.x = fminf(r.x, p.peak);
         r.y = fminf(r.y, p.peak);
         float2 fr;
         if (CENTRAL == 0) {
-            fr = r;
+            fr = __fmul2_rn(r, onf);                                        // pool:172
         } else if (CENTRAL == 1) {
+            // measured on B200: with the adaptation recurrences in the loop the FMA pipe is the busiest
+            // unit, so here the recruitment mask is used as a predicate (scalar, predicated updates)
+            // rather than blended arithmetically (which costs two more FMA-pipe operations per step)
             const float2 q = __ffma2_rn(r, bc(p.phir), bc(-p.phir6));       // pool:231-232
             fr = __ffma2_rn(q, nD[pi], r);                                  // r - q*(1 - exp(-dur/tau)), dur BEFORE the update
-            if (on_a) {                                                     // pool:196-197
+            const bool oa = x.x >= p.crit, ob = x.y >= p.crit;
+            fr.x = oa ? fr.x : 0.0f;                                        // pool:171-172
+            fr.y = ob ? fr.y : 0.0f;
+            if (oa) {                                                       // pool:196-197
                 cnt[pi].x += 1.0f;
                 nD[pi].x = fmaf(nD[pi].x, decay, dm1);
             }
-            if (on_b) {
+            if (ob) {
                 cnt[pi].y += 1.0f;
                 nD[pi].y = fmaf(nD[pi].y, decay, dm1);
             }
         } else {
+            const bool oa = onf.x != 0.0f, ob = onf.y != 0.0f;
             float2 arg = __ffma2_rn(cnt[pi], bc(dtk), make_float2(arg0[2 * pi], arg0[2 * pi + 1]));
-            if (on_a) cnt[pi].x += 1.0f;
-            if (on_b) cnt[pi].y += 1.0f;
-            const float ra = on_a ? r.x : 0.0f, rb = on_b ? r.y : 0.0f;
+            cnt[pi] = __fadd2_rn(cnt[pi], onf);
+            const float ra = oa ? r.x : 0.0f, rb = ob ? r.y : 0.0f;
             fr.x = ra - fmaxf(pool_adaptation(p, ra, fmaxf(arg.x, sc.argmin)), 0.0f);
             fr.y = rb - fmaxf(pool_adaptation(p, rb, fmaxf(arg.y, sc.argmin)), 0.0f);
         }
-        fr.x = on_a ? fr.x : 0.0f;                                          // pool:171-172
-        fr.y = on_b ? fr.y : 0.0f;
+        on_a = onf.x != 0.0f;
+        on_b = onf.y != 0.0f;
         // ---- fibers (fibers:211-259) on ny = -kappa*x: exp(-2x^3) = ex2(ny^3) ----
         const float2 ctkn = __ffma2_rn(cpf[pi], bc(p.ctB), bc(-p.ctA));     // -kappa*ct_cur/1000
         const float2 ny = __fmul2_rn(ctkn, fr);
@@ -223,18 +234,21 @@ struct CoreF32 {
         // ---- capacity update on the compensated pair (fibers:110-114, pmf:94-105) ----
         float2 l = __ffma2_rn(nf, bc(-fatdt), lo[pi]);
         if (FIB == MB_FIBERS_PYMUSCLE) {
-            const float2 gap = __fadd2_rn(room[pi], make_float2(-lo[pi].x, -lo[pi].y));   // peak - capacity
-            float2 g;
-            g.x = (nf.x <= 0.0f) ? gap.x : 0.0f;                            // pmf:121-141
-            g.y = (nf.y <= 0.0f) ? gap.y : 0.0f;
-            l = __ffma2_rn(g, bc(rdidt), l);
+            // recovery of a unit that does not fire (nf <= 0  <=>  not recruited):
+            // l += (peak - capacity) * (1 - onf) * rdidt                    pmf:121-141
+            float2 firing = onf;
+            if (CENTRAL == 2) {                                             // general parameters: test nf itself
+                firing.x = (nf.x > 0.0f) ? 1.0f : 0.0f;
+                firing.y = (nf.y > 0.0f) ? 1.0f : 0.0f;
+            }
+            const float2 gap = __fadd2_rn(room[pi], make_float2(-lo[pi].x, -lo[pi].y));
+            const float2 gn = __ffma2_rn(gap, make_float2(-firing.x, -firing.y), gap);
+            l = __ffma2_rn(gn, bc(rdidt), l);
         }
-        l.x = fmaxf(l.x, -hi[pi].x);
+        l.x = fmaxf(l.x, -hi[pi].x);                                        // fibers:114
         l.y = fmaxf(l.y, -hi[pi].y);
-        if (FIB == MB_FIBERS_PYMUSCLE) {
-            l.x = fminf(l.x, room[pi].x);
-            l.y = fminf(l.y, room[pi].y);
-        }
+        // (the upper clamp at the peak, pmf:104-105, is applied in renormalise(): recovery approaches the
+        //  peak from below and can overshoot it only by rounding)
         lo[pi] = l;
         cpf[pi] = __fadd2_rn(hi[pi], l);
         return F;
@@ -259,6 +273,10 @@ struct CoreF32 {
     __device__ __forceinline__ void renormalise() {
 #pragma unroll
         for (int pi = 0; pi < NP; ++pi) {
+            if (FIB == MB_FIBERS_PYMUSCLE) {                                // pmf:104-105
+                lo[pi].x = fminf(lo[pi].x, room[pi].x);
+                lo[pi].y = fminf(lo[pi].y, room[pi].y);
+            }
             const float2 s1 = __fadd2_rn(hi[pi], lo[pi]);
             const float2 bb = __fadd2_rn(s1, make_float2(-hi[pi].x, -hi[pi].y));
             const float2 t1 = __fadd2_rn(s1, make_float2(-bb.x, -bb.y));
@@ -524,7 +542,7 @@ __device__ __forceinline__ void k2_body(const K2Args& a) {
                     }
                 }
             }
-            if ((tile & 3) == 3) core.renormalise();
+            if ((tile & 3) == 3 || tile == ntiles - 1) core.renormalise();
         }
         __syncwarp();
         // ---- stage 1: this warp's 4 column parts x 8 step rows -> PT[tile & 3] ----------

@@ -27,8 +27,11 @@ constexpr int kWTile = 32;       // steps per tile: lanes of stage 1 = steps
 constexpr int kWPitch = 33;      // row pitch of FTw in float2 (odd => conflict free)
 constexpr int kWarpsPerBlock = 8;
 
+#ifndef MB_W_MINB
+#define MB_W_MINB 2
+#endif
 template <int FIB, int CENTRAL, int UPL, bool FORCES>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 2) k2w_f32(const K2Args a) {
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, MB_W_MINB) k2w_f32(const K2Args a) {
     using Core = CoreF32<FIB, CENTRAL, 2>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
