@@ -350,7 +350,8 @@ def run_gpu_arm(args):
         return 0
 
     ops = OPS_PER_UNIT_STEP["potvin"]
-    achieved = unit_steps * ops / per_launch / 1e12
+    achieved = unit_steps * ops / per_launch / 1e12           # canonical FLOP/s: every add / mul / compare / exp = 1
+    peak_flops = 2.0 * peak_lane_ops / 1e12                   # an FMA lane-op is 2 FLOP
     pipe = "fp32_pipe" if args.precision == "f32" else "fp64_pipe"
     line = {
         "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps,
@@ -358,17 +359,21 @@ def run_gpu_arm(args):
         "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
         "config": workload_config(args), "clocks": clocks, "gpu_launches": gpu_launches, "e2e": e2e,
         "roofline": {
-            "kernel": f"k2_fused_{args.precision}", "bound": pipe, "achieved": achieved,
-            "peak": peak_lane_ops / 1e12, "unit": "Tlane-op/s", "frac": achieved / (peak_lane_ops / 1e12),
-            "traffic": ncu_traffic("k2_fused_f32_config2"),
+            "kernel": ("k2w_f32" if args.precision == "f32" else "k2_fused_f64"), "bound": pipe,
+            "achieved": achieved, "peak": peak_flops, "unit": "TFLOP/s", "frac": achieved / peak_flops,
+            "traffic": ncu_traffic("k2_fused_f32_config2") if args.precision == "f32" else None,
             "ops_per_unit_step": ops,
-            "peak_source": "mb_peak_probe dependent-FMA chains (8 per thread), best of 3, measured in this run; "
-                           "MEASURED_PEAKS.json has no FP32/FP64 pipe figure",
+            "measured_fma_lane_ops_per_s": peak_lane_ops,
+            "frac_vs_lane_op_peak": achieved / (peak_lane_ops / 1e12),
+            "peak_source": "mb_peak_probe dependent-FMA chains (8 per thread), best of 3, measured in this run, x 2 FLOP "
+                           "per FMA; MEASURED_PEAKS.json has no FP32/FP64 pipe figure",
             "note": "achieved = 38 canonical FP operations per unit-step (SURVEY.md A.2 / 8d: the reference's own "
-                    "operation list, FMA not used in the count, exp = 1) x unit-steps per launch / mean launch time; "
-                    "peak = one lane-op per FFMA lane.  The kernel needs fewer issue slots than 38 per unit-step "
-                    "(FMA contraction, packed FFMA2/FMUL2/FADD2, exp(-dur/tau) by recurrence), so frac can exceed 1; "
-                    "profiles/ holds the ncu issue-slot and pipe utilisation of the same launch"},
+                    "operation list; each add, multiply, compare, select and exp counts 1, no FMA contraction) x "
+                    "unit-steps per launch / mean launch time.  The operations are FLOPs, so the peak is the measured "
+                    "FMA lane rate x 2 FLOP.  SURVEY 8d divides by the lane rate instead (frac_vs_lane_op_peak); that "
+                    "figure exceeds 1 because the kernel contracts FMAs, issues packed FFMA2/FMUL2/FADD2 and carries "
+                    "exp(-dur/tau) by recurrence.  profiles/ holds ncu's issue-slot and per-pipe utilisation of the "
+                    "same launch"},
         "roofline_single_step": k1,
         "cpu_baseline": cpu,
         "fused_geometry": batch.fused_geometry(K, args.units_per_thread),
