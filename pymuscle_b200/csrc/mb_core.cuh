@@ -132,6 +132,51 @@ __device__ __forceinline__ double pool_adapt(const UnitD& p, const ScalD& s, dou
     return r - ((a < 0.0) ? 0.0 : a);
 }
 
+// 2^(j/32), j = 0..31 (table of the fast exponential below)
+__constant__ double kExp2Tab[32] = {
+    0x1.0000000000000p+0, 0x1.059b0d3158574p+0, 0x1.0b5586cf9890fp+0, 0x1.11301d0125b51p+0,
+    0x1.172b83c7d517bp+0, 0x1.1d4873168b9aap+0, 0x1.2387a6e756238p+0, 0x1.29e9df51fdee1p+0,
+    0x1.306fe0a31b715p+0, 0x1.371a7373aa9cbp+0, 0x1.3dea64c123422p+0, 0x1.44e086061892dp+0,
+    0x1.4bfdad5362a27p+0, 0x1.5342b569d4f82p+0, 0x1.5ab07dd485429p+0, 0x1.6247eb03a5585p+0,
+    0x1.6a09e667f3bcdp+0, 0x1.71f75e8ec5f74p+0, 0x1.7a11473eb0187p+0, 0x1.82589994cce13p+0,
+    0x1.8ace5422aa0dbp+0, 0x1.93737b0cdc5e5p+0, 0x1.9c49182a3f090p+0, 0x1.a5503b23e255dp+0,
+    0x1.ae89f995ad3adp+0, 0x1.b7f76f2fb5e47p+0, 0x1.c199bdd85529cp+0, 0x1.cb720dcef9069p+0,
+    0x1.d5818dcfba487p+0, 0x1.dfc97337b9b5fp+0, 0x1.ea4afa2a490dap+0, 0x1.f50765b6e4540p+0};
+
+// exp(x) for -700 <= x <= 0 in about a dozen FP64 instructions (the library exp needs ~2.5x
+// as many): x = n*ln2/32 + r, |r| <= ln2/64, exp(x) = 2^(n>>5) * 2^((n&31)/32) * P5(r).
+// Relative error < 1e-14 (truncation r^6/720 = 2e-15, two-step reduction); the FP64 mode's
+// bar is 1e-9.  `tab` is a shared-memory copy of kExp2Tab (divergent index).
+__device__ __forceinline__ double exp_neg_fast(double x, const double* tab) {
+    x = fmax(x, -700.0);
+    const double kMagic = 6755399441055744.0;                          // 1.5 * 2^52: round to integer
+    const double t = fma(x, 0x1.71547652b82fep+5, kMagic);              // x * 32/ln2
+    const int n = __double2loint(t);
+    const double nf = t - kMagic;
+    double r = fma(nf, -0x1.62e42f8000000p-6, x);                       // ln2/32, upper 25 bits (exact product)
+    r = fma(nf, -0x1.be8e7bcd5e4f2p-32, r);                             // ln2/32, remainder
+    double p = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+    p = fma(p, r, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const double s = tab[n & 31] * p;
+    return __hiloint2double(__double2hiint(s) + ((n >> 5) << 20), __double2loint(s));
+}
+
+// fibers_force with the fast exponential (fused kernel)
+__device__ __forceinline__ double fibers_force_fast(const UnitD& p, const ScalD& s, double fr, double cpf, double& nf,
+                                                    const double* tab) {
+    const double ctk = fma(cpf, -p.ctB, p.ctA);
+    const double x = ctk * fr;
+    if (x <= kLinThrD) {
+        nf = x * s.c25;
+    } else {
+        nf = 1.0 - exp_neg_fast(-2.0 * (x * x * x), tab);
+    }
+    return nf * cpf;
+}
+
 __device__ __forceinline__ double fibers_force(const UnitD& p, const ScalD& s, double fr, double cpf, double& nf) {
     const double ctk = fma(cpf, -p.ctB, p.ctA);
     const double x = ctk * fr;

@@ -269,6 +269,7 @@ struct CoreF32 {
         }
     }
 
+    __device__ __forceinline__ void set_table(const double*) {}
     // renormalise (TwoSum) so that |lo| <= ulp(hi)/2 again
     __device__ __forceinline__ void renormalise() {
 #pragma unroll
@@ -320,6 +321,7 @@ struct CoreF64 {
     ScalD sc;
     double fatdt, rdidt, dt, max_dur, decay, Emax;
     double cpf[U], dur[U], E[U];
+    const double* tab;           // shared-memory copy of kExp2Tab
 
     __device__ __forceinline__ void load(const K2Args& a, int u) {
         p = load_unit((const double2*)a.params, a.n, u);
@@ -360,7 +362,7 @@ struct CoreF64 {
             }
         }
         double nf;
-        const double F = fibers_force(p, sc, fr, cpf[j], nf);
+        const double F = fibers_force_fast(p, sc, fr, cpf[j], nf, tab);
         cpf[j] = fatigue_update<FIB == MB_FIBERS_PYMUSCLE>(cpf[j], nf, fatdt, rdidt, p.ptf);
         return F;
     }
@@ -374,6 +376,7 @@ struct CoreF64 {
         }
     }
     __device__ __forceinline__ void renormalise() {}
+    __device__ __forceinline__ void set_table(const double* t) { tab = t; }
     __device__ __forceinline__ void store(int j, const K2Args& a, int64_t idx) {
         if (a.peripheral) a.cpf[idx] = cpf[j];
         if (CENTRAL) a.dur[idx] = dur[j];
@@ -434,6 +437,8 @@ __device__ __forceinline__ void k2_body(const K2Args& a) {
     const int64_t m0 = (int64_t)blockIdx.x * a.G;
     const int gcount = (int)min((int64_t)a.G, a.M - m0);
     const int ntiles = (a.K + a.T - 1) / a.T;
+    __shared__ double exp2_tab[32];                       // for exp_neg_fast (FP64 mode)
+    if (tid < 32) exp2_tab[tid] = kExp2Tab[tid];
 
     if (tid == 0) {
         for (int i = 0; i < kExcSlots; ++i) mbar_init(exc_bar0 + 8u * i, 1);
@@ -466,6 +471,7 @@ __device__ __forceinline__ void k2_body(const K2Args& a) {
     const bool has_unit = tq < a.q && u_raw < n;
     const int u = has_unit ? u_raw : 0;
     Core core;
+    core.set_table(exp2_tab);
     core.load(a, u);
 #pragma unroll
     for (int j = 0; j < U; ++j) {
