@@ -698,11 +698,10 @@ static int fused_geometry(const MbConfig& c, int64_t M, int32_t n, int32_t K, in
     const int ns = (n + 7) / 8 * 8;                          // threads per muscle group (stage-1 parts are 8 wide)
     int q = kFusedMaxUnits / ns;
     if (upt != 0 && upt != 1 && upt != 2 && upt != 4) return fail(MB_EINVAL, "units_per_thread must be 0, 1, 2 or 4");
-    if (!f32 && upt == 4) return fail(MB_EINVAL, "units_per_thread 4 is FP32-only");
     int U = upt;
     if (U == 0) {
         // largest U that still leaves >= 2 blocks per SM; small batches spread out instead
-        U = f32 ? 4 : 2;
+        U = 4;
         while (U > 1 && (M + (int64_t)q * U - 1) / ((int64_t)q * U) < 2LL * sm_count()) U >>= 1;
     }
     // a block should not own more muscles than exist
@@ -829,6 +828,7 @@ extern "C" int mb_step_fused(const MbConfig* cfg, const void* params_dev, int64_
         return MB_DISPATCH_FIB(k2_fused_f32, 1);
     }
     if (cen == 2) cen = 1;      // FP64 always applies both clamps (duration_update / pool_adapt)
+    if (g.U == 4) return MB_DISPATCH_FIB64(4);
     if (g.U == 2) return MB_DISPATCH_FIB64(2);
     return MB_DISPATCH_FIB64(1);
 }

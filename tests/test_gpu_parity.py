@@ -150,8 +150,6 @@ def test_fused_equals_single_step_and_decimated_forces(cuda_device, precision):
 @pytest.mark.parametrize("precision", ["f32", "f64"])
 @pytest.mark.parametrize("upt", [1, 2, 4])
 def test_fused_units_per_thread_variants(cuda_device, precision, upt):
-    if precision == "f64" and upt == 4:
-        pytest.skip("4 units per thread is FP32-only")
     rng = np.random.default_rng(upt)
     m, n, K = 70, 120, 40
     exc = (67.0 * rng.random((K, m))).astype(np.float32)
