@@ -27,9 +27,9 @@ struct UnitF {
     float ctB;     // kappa * ct * ccr / (1000 * ptf):  kappa*ct_cur/1000 = ctA - ctB*cpf  (fibers:123-125, :220)
     float fat;     // nominal fatigability                                             (fibers:110)
     float ptf;     // peak twitch force (upper clamp)                                  (pmf:104-105)
-    float rec;     // recovery rate                                                    (pmf:140)
+    float ptf_lo2; // third float of the peak: ptf + ptf_lo + ptf_lo2 is the float64 peak exactly
     float rdi;     // rec / ptf:  recovery = (ptf - cpf) * rdi * dt                    (pmf:137-140)
-    float ptf_lo;  // ptf - (float)ptf, so that ptf + ptf_lo carries 48 bits of the float64 peak
+    float ptf_lo;  // (float)(peak - ptf): ptf + ptf_lo carries 48 bits of the float64 peak
 };
 
 struct UnitD {
@@ -41,7 +41,7 @@ __device__ __forceinline__ UnitF load_unit(const float4* __restrict__ P, int64_t
     UnitF u;
     u.crit = a.x; u.thr_g = a.y; u.peak = a.z; u.phir = a.w;
     u.phir6 = b.x; u.ctA = b.y; u.ctB = b.z; u.fat = b.w;
-    u.ptf = c.x; u.rec = c.y; u.rdi = c.z; u.ptf_lo = c.w;
+    u.ptf = c.x; u.ptf_lo2 = c.y; u.rdi = c.z; u.ptf_lo = c.w;
     return u;
 }
 
@@ -219,5 +219,9 @@ __device__ __forceinline__ double warp_sum(double v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+
+// the float64 peak twitch force, exactly (a rested unit has capacity == peak, and must keep it)
+__device__ __forceinline__ double unit_peak(const UnitF& p) { return ((double)p.ptf + (double)p.ptf_lo) + (double)p.ptf_lo2; }
+__device__ __forceinline__ double unit_peak(const UnitD& p) { return p.ptf; }
 
 }  // namespace mb

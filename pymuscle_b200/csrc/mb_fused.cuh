@@ -153,7 +153,7 @@ struct CoreF32 {
 #pragma unroll
         for (int j = 0; j < 2 * NP; ++j) init(j, a, rest_capacity(), 0.0);   // the idle half of an odd U
     }
-    __device__ __forceinline__ double rest_capacity() const { return (double)p.ptf + (double)p.ptf_lo; }
+    __device__ __forceinline__ double rest_capacity() const { return unit_peak(p); }
     __device__ __forceinline__ void init(int j, const K2Args& a, double c, double d0) {
         const int pi = j >> 1, k = j & 1;
         const float h = (float)c;

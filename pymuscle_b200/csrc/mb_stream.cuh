@@ -83,8 +83,6 @@ __device__ __forceinline__ double k1s_unit(const K1sArgs<double>& a, const UnitD
     cn = fatigue_update<RECOVERY>(c, nf, fatdt, rdidt, ptf);
     return F;
 }
-__device__ __forceinline__ double unit_ptf(const UnitF& p) { return (double)p.ptf + (double)p.ptf_lo; }
-__device__ __forceinline__ double unit_ptf(const UnitD& p) { return p.ptf; }
 
 template <typename T, bool CENTRAL, bool RECOVERY, bool FORCES>
 __global__ void __launch_bounds__(288, 2) k1_stream(const K1sArgs<T> a) {
@@ -174,7 +172,7 @@ __global__ void __launch_bounds__(288, 2) k1_stream(const K1sArgs<T> a) {
             const bool active = u < n;
             const auto p = load_unit(a.params, a.L, off0 + (active ? u : 0));
             const double fatdt = (double)p.fat * a.dt, rdidt = (double)p.rdi * a.dt;
-            const double ptf = unit_ptf(p);
+            const double ptf = unit_peak(p);
             const int shift = (off0 + u0) & 1;
             mbar_wait(bar0 + 8u * s, ph);
             if (active) {

@@ -148,7 +148,10 @@ extern "C" int mb_params_pack(const MbConfig* cfg, int64_t L, const double* thr,
             P[i] = make_float4(critical_input(cfg->input_scale, thr[i], minr), (float)(g * (thr[i] - minr)),
                                (float)peak[i], (float)phir);
             P[L + i] = make_float4((float)phir6, (float)(ctA * kKappa), (float)(ctB * kKappa), (float)fat[i]);
-            P[2 * L + i] = make_float4((float)ptf[i], (float)r, (float)rdi, (float)(ptf[i] - (double)(float)ptf[i]));
+            const float p0 = (float)ptf[i];
+            const float p1 = (float)(ptf[i] - (double)p0);
+            const float p2 = (float)((ptf[i] - (double)p0) - (double)p1);          // p0 + p1 + p2 == ptf[i] exactly
+            P[2 * L + i] = make_float4(p0, p2, (float)rdi, p1);
         } else {
             double2* P = (double2*)out_host;
             P[i] = make_double2(thr[i], peak[i]);
@@ -222,7 +225,7 @@ __device__ __forceinline__ float k1_compute(const K1Args<float>& a, const UnitF&
     const float F = fibers_force(p, a.sc, fr, (float)c, nf);
     if (a.peripheral) {
         const double fatdt = (double)p.fat * a.dt, rdidt = (double)p.rdi * a.dt;
-        const double ptf = (double)p.ptf + (double)p.ptf_lo;
+        const double ptf = unit_peak(p);
         o.c_new = a.recovery ? fatigue_update<true>(c, (double)nf, fatdt, rdidt, ptf)
                              : fatigue_update<false>(c, (double)nf, fatdt, rdidt, ptf);
     }

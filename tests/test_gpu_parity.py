@@ -273,3 +273,85 @@ def test_state_dict_roundtrip_and_fresh_outputs(cuda_device):
     assert torch.equal(a.cpf, b.cpf)
     b.reset()
     assert torch.equal(b.cpf[0], torch.from_numpy(spec.tables()["ptf"]).to(cuda_device))
+
+
+def test_full_size_properties_config5(cuda_device):
+    """BASELINE config #5 at full size: StandardMuscle with 2,000 units x 131,072 instances, one
+    launch per frame (the HBM streaming kernel), FP32 mode.  (i) equal inputs give equal
+    outputs anywhere in the batch; (ii) a sample matches the oracle; (iii) capacities stay in
+    [0, peak]; (iv) resting muscles keep their exact state."""
+    M, dt, frames = 131072, 0.02, 4
+    spec = MuscleSpec.standard(527.1)
+    assert spec.n == 2000
+    rng = np.random.default_rng(5)
+    levels = rng.random((frames, 32)).astype(np.float32)
+    levels[:, 0] = 0.0
+    idx = rng.integers(0, 32, size=M)
+    idx[:32] = np.arange(32)
+    b = MuscleBatch(spec, M, cuda_device, "f32", fresh_outputs=False)
+    ora = OracleMuscles.standard(527.1, m=32)
+    ptf = ora.t.ptf
+    for k in range(frames):
+        tot = b.step(torch.from_numpy(levels[k][idx]).to(cuda_device), dt)
+        want = ora.step(levels[k].astype(np.float64), dt)
+        tot = tot.cpu().numpy()
+        for lv in (0, 7, 31):                                                  # (i)
+            cols = np.nonzero(idx == lv)[0]
+            assert (tot[cols] == tot[cols[0]]).all()
+        close(tot[:32], want.total, "f32", 1.0, f"sampled totals, frame {k}")  # (ii)
+        close(b.current_forces[:32].cpu().numpy(), want.forces, "f32", ptf, f"sampled forces, frame {k}")
+    cpf = b.cpf
+    close(cpf[:32].cpu().numpy(), ora.cpf, "f32", ptf, "sampled capacities")
+    peak = torch.from_numpy(ptf).to(cuda_device)
+    assert bool((cpf <= peak[None]).all()) and bool((cpf >= 0).all())         # (iii)
+    zero = torch.from_numpy(np.nonzero(idx == 0)[0]).to(cuda_device)            # (iv)
+    assert bool((cpf[zero] == peak[None]).all())
+
+
+def test_full_size_properties_config3(cuda_device):
+    """BASELINE config #3 at full size: the 30-muscle arm (35,032 units) x 4,096 agents, per-step
+    random excitation per (agent, muscle), single-step launches on the ragged layout, FP32 mode."""
+    g = golden("arm")
+    specs = [MuscleSpec.standard(max_force=float(f)) for f in g["max_forces"]]
+    agents, dt, frames = 4096, 0.02, 3
+    rng = np.random.default_rng(3)
+    b = MuscleBatch(specs, agents, cuda_device, "f32", fresh_outputs=False)
+    assert b.n_units == 4096 * 35032 and b.n_muscles == 122880
+    oras = [OracleMuscles.standard(float(f), m=4) for f in g["max_forces"]]
+    for k in range(frames):
+        exc = rng.random((agents, 30)).astype(np.float32)
+        exc[1] = exc[0]                                                         # two identical agents
+        tot = b.step(torch.from_numpy(exc).to(cuda_device), dt).cpu().numpy()
+        assert tot.shape == (agents, 30) and np.array_equal(tot[0], tot[1])
+        for s, o in enumerate(oras):                                            # agents 0..3 against the oracle
+            want = o.step(exc[:4, s].astype(np.float64), dt)
+            close(tot[:4, s], want.total, "f32", 1.0, f"arm totals, muscle {s}, frame {k}")
+    off = np.cumsum([0] + [s.n for s in specs])
+    cpf = b.cpf[:4].cpu().numpy()
+    for s, o in enumerate(oras):
+        close(cpf[:, off[s]:off[s + 1]], o.cpf, "f32", o.t.ptf, f"arm capacities, muscle {s}")
+    assert np.array_equal(b.cpf[0].cpu().numpy(), b.cpf[1].cpu().numpy())
+
+
+def test_full_size_properties_config4_shard(cuda_device):
+    """BASELINE config #4, one GPU's shard (32,768 PotvinFuglevandMuscle(120), FP64 mode): the
+    ramp-hold-rest protocol compressed to 1,500 steps, run as fused windows of 500; a sample of
+    muscles against the oracle at rtol 1e-9, masks of the last step bit-exact."""
+    M, n, dt, K = 32768, 120, 0.02, 1500
+    rng = np.random.default_rng(4)
+    e_max = 67.0 * (0.5 + 0.5 * rng.random(M))
+    k = np.arange(K)
+    shape = np.where(k < 300, k / 300.0, np.where(k < 900, 1.0, 0.0))          # ramp, hold, rest
+    b = MuscleBatch(MuscleSpec.potvin(n), M, cuda_device, "f64", fresh_outputs=False)
+    ora = OracleMuscles(n, 16, "potvin")
+    em = torch.from_numpy(e_max).to(cuda_device)
+    sh = torch.from_numpy(shape).to(cuda_device)
+    tots = []
+    for w in range(0, K, 500):
+        exc = sh[w:w + 500, None] * em[None, :]
+        tots.append(b.step_many(exc, dt)[:, :16].cpu().numpy())
+    want = np.stack([ora.step(shape[i] * e_max[:16], dt).total for i in range(K)])
+    close(np.concatenate(tots), want, "f64", 2609.03, "sampled totals")
+    close(b.cpf[:16].cpu().numpy(), ora.cpf, "f64", ora.t.ptf, "sampled capacities")
+    np.testing.assert_allclose(b.dur[:16].cpu().numpy(), ora.dur, rtol=1e-9, atol=1e-12)
+    assert bool((b.cpf <= torch.from_numpy(ora.t.ptf).to(cuda_device)[None]).all())
