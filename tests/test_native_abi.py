@@ -114,10 +114,21 @@ def test_fused_geometry_for_the_headline_config():
     lib = nat.lib()
     cfg = pack_row([MuscleSpec.potvin(120)], nat.MB_F32).cfg
     mpb, thr, smem, blocks = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int64()
+    # auto: the warp kernel (one warp per pair of muscles, 8 warps per block)
     nat.check(lib.mb_fused_geometry(C.byref(cfg), 65536, 120, 1000, 0, C.byref(mpb), C.byref(thr),
                                     C.byref(blocks), C.byref(smem)))
-    assert thr.value == 480 and mpb.value == 16 and blocks.value == 4096      # 4 groups x 120 threads = 15 full warps
+    assert thr.value == 256 and mpb.value == 16 and blocks.value == 4096
     assert smem.value <= 110 * 1024                                           # two blocks per SM
+    # explicit units_per_thread: the block kernel, 4 groups x 120 threads = 15 full warps
+    nat.check(lib.mb_fused_geometry(C.byref(cfg), 65536, 120, 1000, 4, C.byref(mpb), C.byref(thr),
+                                    C.byref(blocks), C.byref(smem)))
+    assert thr.value == 480 and mpb.value == 16 and blocks.value == 4096
+    assert smem.value <= 110 * 1024
+    # FP64 mode: 4 instances per thread, one block per SM
+    cfg64 = pack_row([MuscleSpec.potvin(120)], nat.MB_F64).cfg
+    nat.check(lib.mb_fused_geometry(C.byref(cfg64), 32768, 120, 1000, 0, C.byref(mpb), C.byref(thr),
+                                    C.byref(blocks), C.byref(smem)))
+    assert thr.value == 480 and mpb.value == 16 and smem.value <= 220 * 1024
 
 
 def test_missing_library_fails_loudly(monkeypatch):
