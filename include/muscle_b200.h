@@ -131,6 +131,24 @@ int mb_step(const MbConfig* cfg, const void* params_dev,
             void* forces_dev, void* totals_dev, uint8_t* mask_dev, void* rates_dev,
             double step_size, void* stream);
 
+/* ---- K1 with a fused per-muscle epilogue (vector-environment step) ----------------------
+ * One launch replaces, for every muscle of every row, the loop bodies of the reference's
+ * environment examples: outputs = [muscle.step(a[i], dt) for i, muscle in enumerate(muscles)]
+ * (examples/envs/muscled_hopper.py:33-34, examples/envs/pymunk_arm.py:165-166) followed by
+ * StandardMuscle.get_peripheral_fatigue() (muscle.py:248-256) as the proprioceptive signal, with
+ * an optional per-muscle output multiplier (e.g. the Hill-type force-length / force-velocity
+ * factors of pymuscle/hill_type.py:15-66).
+ *   in_dev        [rows, S] one excitation per muscle
+ *   out_gain_dev  [rows, S] totals are multiplied by it; may be NULL
+ *   fatigue_dev   [rows, S] float64, 1 - sum(new capacities)/output divisor; may be NULL
+ * Returns MB_EUNSUPPORTED for layouts the streaming kernel does not cover (odd row length,
+ * unaligned state, peripheral fatigue off); the caller then uses mb_step + mb_peripheral_fatigue. */
+int mb_step_env(const MbConfig* cfg, const void* params_dev,
+                int64_t rows, int64_t L, int32_t S, const int32_t* seg_off_dev, const double* seg_div_dev,
+                const void* in_dev, double* cpf_dev, double* dur_dev,
+                void* forces_dev, void* totals_dev, const void* out_gain_dev, double* fatigue_dev,
+                double step_size, void* stream);
+
 /* ---- K2: K fused steps, state in registers (FP32/FP64-pipe-bound) --------------------
  * Equivalent to K successive Muscle.step calls on each of `M` identical muscles of `n`
  * units (uniform layout only: rows = M, L = n, S = 1).

@@ -15,3 +15,6 @@ from .models import PyMuscleFibers  # noqa: F401
 from .engine import MuscleBatch  # noqa: F401
 from .tables import MuscleSpec, PoolParams, FibersParams  # noqa: F401
 from .distributed import ShardedMuscleBatch, shard_bounds  # noqa: F401
+from .hill_type import contractile_element_force_velocity_curve  # noqa: F401
+from .hill_type import contractile_element_force_length_curve  # noqa: F401
+from .envs import MuscleGroupEnv  # noqa: F401

@@ -47,7 +47,10 @@ struct K1sArgs {
     double* dur;
     T* forces;                   // may be NULL
     T* totals;                   // may be NULL
+    const T* out_gain;           // [rows, S] multiplier of the totals (e.g. Hill-type factors); may be NULL
+    double* fatigue;             // [rows, S] 1 - sum(new capacity)/divisor (muscle.py:248-256); may be NULL
     double dt, adk_d, max_dur;
+    double fat_div;              // output divisor of a uniform batch (seg_div == NULL)
     typename StreamTraits<T>::S sc;
 };
 
@@ -84,7 +87,7 @@ __device__ __forceinline__ double k1s_unit(const K1sArgs<double>& a, const UnitD
     return F;
 }
 
-template <typename T, bool CENTRAL, bool RECOVERY, bool FORCES>
+template <typename T, bool CENTRAL, bool RECOVERY, bool FORCES, bool FATIGUE>
 __global__ void __launch_bounds__(288, 2) k1_stream(const K1sArgs<T> a) {
     constexpr int R = kStreamRows;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -93,7 +96,7 @@ __global__ void __launch_bounds__(288, 2) k1_stream(const K1sArgs<T> a) {
     const uint32_t bar0 = smem_u32(smem_raw);             // full[NS] | empty[NS]
     double* cpf_s = (double*)(smem_raw + 128);            // [NS][R][rowp]
     double* dur_s = cpf_s + (size_t)NS * R * rowp;        // [NS][R][rowp]   (CENTRAL only)
-    T* red = (T*)(CENTRAL ? dur_s + (size_t)NS * R * rowp : dur_s);   // [R][8]
+    T* red = (T*)(CENTRAL ? dur_s + (size_t)NS * R * rowp : dur_s);   // [2R][8]: force sums | capacity sums
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ncons = blockDim.x - 32;                    // consumer threads (== W)
@@ -159,12 +162,14 @@ __global__ void __launch_bounds__(288, 2) k1_stream(const K1sArgs<T> a) {
         const int off0 = a.seg_off ? a.seg_off[seg] : 0;
         const int n = a.seg_off ? a.seg_off[seg + 1] - off0 : (int)a.L;
         const int nrows = (int)min((int64_t)R, a.rows - r0);
-        T xm[R], partial[R];
+        T xm[R], partial[R], csum[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             partial[r] = 0;
+            csum[r] = 0;
             xm[r] = xnext[r];
         }
+        constexpr bool want_fatigue = FATIGUE;                // fused get_peripheral_fatigue epilogue
         fetch_inputs(item + gridDim.x, xnext);
         for (int u0 = 0; u0 < n; u0 += W, ++it) {
             const uint32_t s = it % NS, ph = (it / NS) & 1;
@@ -195,6 +200,7 @@ __global__ void __launch_bounds__(288, 2) k1_stream(const K1sArgs<T> a) {
                     *cp = cn;
                     if (CENTRAL) *dp = dn;
                     partial[r] += F;
+                    if (want_fatigue) csum[r] += (T)cn;
                     if (FORCES) fp += a.L;
                     cp += a.L;
                     if (CENTRAL) dp += a.L;
@@ -211,17 +217,33 @@ __global__ void __launch_bounds__(288, 2) k1_stream(const K1sArgs<T> a) {
             __syncwarp();
             if (lane == 0) mbar_arrive(bar0 + 8u * (NS + s));    // this warp is done with the stage
         }
-        if (a.totals) {
+        if (a.totals || want_fatigue) {
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const T w = warp_sum(partial[r]);
                 if (lane == 0) red[r * 8 + warp] = w;
             }
+            if (want_fatigue) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const T w = warp_sum(csum[r]);
+                    if (lane == 0) red[(R + r) * 8 + warp] = w;
+                }
+            }
             asm volatile("bar.sync 1, %0;" ::"r"(ncons) : "memory");
             if (tid < nrows) {
-                T sum = red[tid * 8];
-                for (int w = 1; w < ncw; ++w) sum += red[tid * 8 + w];
-                a.totals[(r0 + tid) * a.S + seg] = a.seg_div ? out_div(sum, a.seg_div[seg]) : out_scale(a.sc, sum);
+                const int64_t mu = (r0 + tid) * a.S + seg;
+                if (a.totals) {
+                    T sum = red[tid * 8];
+                    for (int w = 1; w < ncw; ++w) sum += red[tid * 8 + w];
+                    sum = a.seg_div ? out_div(sum, a.seg_div[seg]) : out_scale(a.sc, sum);
+                    a.totals[mu] = a.out_gain ? sum * a.out_gain[mu] : sum;      // epilogue: Hill-type factors etc.
+                }
+                if (want_fatigue) {
+                    double cs = (double)red[(R + tid) * 8];
+                    for (int w = 1; w < ncw; ++w) cs += (double)red[(R + tid) * 8 + w];
+                    a.fatigue[mu] = 1.0 - cs / (a.seg_div ? a.seg_div[seg] : a.fat_div);
+                }
             }
             asm volatile("bar.sync 1, %0;" ::"r"(ncons) : "memory");
         }

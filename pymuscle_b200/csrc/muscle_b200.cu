@@ -565,9 +565,9 @@ static int launch_k1(const MbConfig& c, const void* params, int64_t rows, int64_
 }
 
 // ---- K1s launcher ---------------------------------------------------------------------------
-template <typename T, bool CENTRAL, bool RECOVERY, bool FORCES>
+template <typename T, bool CENTRAL, bool RECOVERY, bool FORCES, bool FATIGUE>
 static int launch_k1s_variant(const K1sArgs<T>& a, int threads, int smem, int64_t items, cudaStream_t st) {
-    auto kern = k1_stream<T, CENTRAL, RECOVERY, FORCES>;
+    auto kern = k1_stream<T, CENTRAL, RECOVERY, FORCES, FATIGUE>;
     if (smem > 48 * 1024) MB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     // persistent grid: exactly the blocks that are resident at once, each walking the work list
     int per_sm = 0;
@@ -597,12 +597,14 @@ static bool k1s_eligible(const MbConfig& c, int64_t L, int32_t stage, int32_t in
 template <typename T>
 static int launch_k1s(const MbConfig& c, const void* params, int64_t rows, int64_t L, int32_t S,
                       const int32_t* seg_off, const double* seg_div, const void* in, double* cpf, double* dur,
-                      void* forces, void* totals, double dt, cudaStream_t st, const typename Vec<T>::S& sc) {
+                      void* forces, void* totals, const void* out_gain, double* fatigue, double dt, cudaStream_t st,
+                      const typename Vec<T>::S& sc) {
     K1sArgs<T> a;
     a.params = (const typename StreamTraits<T>::P*)params;
     a.rows = rows; a.L = L; a.S = S; a.seg_off = seg_off; a.seg_div = seg_div;
     a.peripheral = c.peripheral_fatigue != 0;
     a.in = (const T*)in; a.cpf = cpf; a.dur = dur; a.forces = (T*)forces; a.totals = (T*)totals;
+    a.out_gain = (const T*)out_gain; a.fatigue = fatigue; a.fat_div = c.output_divisor;
     a.dt = dt;
     a.adk_d = -kLog2e / c.adaptation_time_constant;
     a.max_dur = c.max_duration;
@@ -620,12 +622,14 @@ static int launch_k1s(const MbConfig& c, const void* params, int64_t rows, int64
     if (NS < 2) NS = 2;
     a.W = W; a.NS = NS;
     const int threads = W + 32;
-    const int smem = 128 + NS * stage_bytes + kStreamRows * 8 * (int)sizeof(T);
+    const int smem = 128 + NS * stage_bytes + 2 * kStreamRows * 8 * (int)sizeof(T);
     const int64_t items = ((rows + kStreamRows - 1) / kStreamRows) * S;
-#define MB_K1S(C_, R_) (forces ? launch_k1s_variant<T, C_, R_, true>(a, threads, smem, items, st) \
-                               : launch_k1s_variant<T, C_, R_, false>(a, threads, smem, items, st))
+#define MB_K1S_F(C_, R_, F_) (fatigue ? launch_k1s_variant<T, C_, R_, F_, true>(a, threads, smem, items, st) \
+                                       : launch_k1s_variant<T, C_, R_, F_, false>(a, threads, smem, items, st))
+#define MB_K1S(C_, R_) (forces ? MB_K1S_F(C_, R_, true) : MB_K1S_F(C_, R_, false))
     if (central) return recovery ? MB_K1S(true, true) : MB_K1S(true, false);
     return recovery ? MB_K1S(false, true) : MB_K1S(false, false);
+#undef MB_K1S_F
 #undef MB_K1S
 }
 
@@ -645,15 +649,39 @@ extern "C" int mb_step(const MbConfig* cfg, const void* params_dev, int64_t rows
     if (cfg->precision == MB_F32) {
         if (k1s_eligible<float>(*cfg, L, stage, in_per_unit, cpf_dev, dur_dev, mask_dev, rates_dev))
             return launch_k1s<float>(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, in_dev, cpf_dev, dur_dev,
-                                     forces_dev, totals_dev, step_size, st, scal_f(*cfg));
+                                     forces_dev, totals_dev, nullptr, nullptr, step_size, st, scal_f(*cfg));
         return launch_k1<float>(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, stage, in_dev, in_per_unit, cpf_dev,
                                 dur_dev, forces_dev, totals_dev, mask_dev, rates_dev, step_size, st, scal_f(*cfg));
     }
     if (k1s_eligible<double>(*cfg, L, stage, in_per_unit, cpf_dev, dur_dev, mask_dev, rates_dev))
         return launch_k1s<double>(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, in_dev, cpf_dev, dur_dev,
-                                  forces_dev, totals_dev, step_size, st, scal_d(*cfg));
+                                  forces_dev, totals_dev, nullptr, nullptr, step_size, st, scal_d(*cfg));
     return launch_k1<double>(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, stage, in_dev, in_per_unit, cpf_dev, dur_dev,
                              forces_dev, totals_dev, mask_dev, rates_dev, step_size, st, scal_d(*cfg));
+}
+
+// Whole-muscle step with a fused epilogue: totals *= out_gain (per muscle) and, in the same pass,
+// the peripheral fatigue of the NEW capacities.  Streaming kernel only (see k1s_eligible).
+extern "C" int mb_step_env(const MbConfig* cfg, const void* params_dev, int64_t rows, int64_t L, int32_t S,
+                           const int32_t* seg_off_dev, const double* seg_div_dev, const void* in_dev,
+                           double* cpf_dev, double* dur_dev, void* forces_dev, void* totals_dev,
+                           const void* out_gain_dev, double* fatigue_dev, double step_size, void* stream) {
+    if (int rc = check_cfg(cfg)) return rc;
+    if (!params_dev || !in_dev || !cpf_dev) return fail(MB_EINVAL, "mb_step_env: params/in/cpf is NULL");
+    if (rows <= 0 || L <= 0 || S <= 0) return fail(MB_EINVAL, "mb_step_env: rows, L, S must be positive");
+    if (S > 1 && !seg_off_dev) return fail(MB_EINVAL, "mb_step_env: seg_off required when S > 1");
+    if (cfg->central_fatigue && !dur_dev) return fail(MB_EINVAL, "mb_step_env: dur is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cfg->precision == MB_F32) {
+        if (!k1s_eligible<float>(*cfg, L, MB_STAGE_MUSCLE, 0, cpf_dev, dur_dev, nullptr, nullptr))
+            return fail(MB_EUNSUPPORTED, "mb_step_env needs an even row length, 16-byte aligned state and peripheral fatigue on");
+        return launch_k1s<float>(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, in_dev, cpf_dev, dur_dev,
+                                 forces_dev, totals_dev, out_gain_dev, fatigue_dev, step_size, st, scal_f(*cfg));
+    }
+    if (!k1s_eligible<double>(*cfg, L, MB_STAGE_MUSCLE, 0, cpf_dev, dur_dev, nullptr, nullptr))
+        return fail(MB_EUNSUPPORTED, "mb_step_env needs an even row length, 16-byte aligned state and peripheral fatigue on");
+    return launch_k1s<double>(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, in_dev, cpf_dev, dur_dev,
+                              forces_dev, totals_dev, out_gain_dev, fatigue_dev, step_size, st, scal_d(*cfg));
 }
 
 extern "C" int mb_peripheral_fatigue(const MbConfig* cfg, int64_t rows, int64_t L, int32_t S,

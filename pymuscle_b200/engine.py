@@ -155,6 +155,40 @@ class MuscleBatch:
             self._forces = forces
         return self._shape_out(out.view(self.rows, self.S))
 
+    # ---- K1 with the fused environment epilogue -------------------------------------------
+    def step_env(self, excitation, step_size: float, gain: Optional[torch.Tensor] = None,
+                 want_fatigue: bool = True):
+        """One step for a vector environment: per-muscle totals (optionally multiplied by
+        ``gain``, e.g. Hill-type force-length x force-velocity factors) and the peripheral
+        fatigue of every muscle after the step, in ONE launch (mb_step_env).
+
+        Equivalent to ``[m.step(a, dt) for m in muscles]`` followed by
+        ``[m.get_peripheral_fatigue() for m in muscles]`` over every agent
+        (examples/envs/muscled_hopper.py:33-34, muscle.py:248-256).
+        Returns ``(totals, fatigue)``; fatigue is float64 (None if not wanted)."""
+        x, per_unit = self._as_input(excitation, per_unit_ok=False)
+        out = torch.empty(self.rows, self.S, dtype=self.dtype, device=self.device)
+        forces = torch.empty_like(self._forces) if self.fresh_outputs else self._forces
+        fat = torch.empty(self.rows, self.S, dtype=torch.float64, device=self.device) if want_fatigue else None
+        g = None
+        if gain is not None:
+            g = gain.to(device=self.device, dtype=self.dtype).reshape(self.rows, self.S).contiguous()
+        try:
+            with torch.cuda.device(self.device):
+                nat.check(nat.lib().mb_step_env(
+                    C.byref(self.cfg), _ptr(self._params), self.rows, self.L, self.S,
+                    _ptr(self._seg_off), _ptr(self._seg_div), _ptr(x), _ptr(self.cpf), _ptr(self.dur),
+                    _ptr(forces), _ptr(out), _ptr(g), _ptr(fat), float(step_size), self._stream()))
+            self.launches += 1
+            self._forces = forces
+        except nat.UnsupportedError:                         # layouts the streaming kernel does not cover
+            out = self.step(x, step_size).view(self.rows, self.S)
+            if g is not None:
+                out = out * g
+            if want_fatigue:
+                fat = self.get_peripheral_fatigue().view(self.rows, self.S)
+        return self._shape_out(out), (self._shape_out(fat) if fat is not None else None)
+
     # ---- K2: K fused steps ------------------------------------------------------------
     def step_many(self, excitations, step_size: float, steps: Optional[int] = None,
                   out: Optional[torch.Tensor] = None, forces_every: int = 0,

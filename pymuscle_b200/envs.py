@@ -1,0 +1,65 @@
+"""
+Vector-environment adapter: the muscles of many agents advanced by one launch per env step.
+
+The reference's environments keep a Python list of muscles per agent and loop over it every
+step -- ``outputs = [muscle.step(a[i], dt) for i, muscle in enumerate(self.muscles)]``
+(examples/envs/muscled_hopper.py:29-36; examples/envs/pymunk_arm.py:150-179 does the same
+for two muscles) -- and a vector env repeats that per agent.  ``MuscleGroupEnv`` holds the same
+muscles for ``agents`` copies on the GPU: ``step(actions)`` is one streaming-kernel launch that
+returns every muscle's output and, as the proprioceptive observation the library offers
+(README "fatigue" signal, muscle.py:248-256), every muscle's peripheral fatigue.  With
+``rest_lengths`` set, outputs are scaled by the Hill-type force-length and force-velocity
+factors (pymuscle/hill_type.py) of the muscle lengths the physics reports.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Union
+
+import torch
+
+from .engine import MuscleBatch
+from .hill_type import (contractile_element_force_length_curve,
+                        contractile_element_force_velocity_curve)
+from .tables import MuscleSpec
+
+
+class MuscleGroupEnv:
+    """``agents`` copies of a group of muscles.
+
+    specs         the group (e.g. 4 StandardMuscles of a hopper leg, 30 of an arm)
+    agents        number of environment copies
+    rest_lengths  optional [S] (or [agents, S]) resting lengths: enables the Hill-type scaling
+    """
+
+    def __init__(self, specs: Union[MuscleSpec, Sequence[MuscleSpec]], agents: int, device=None,
+                 precision: str = "f32", rest_lengths: Optional[torch.Tensor] = None):
+        self.specs = [specs] if isinstance(specs, MuscleSpec) else list(specs)
+        self.batch = MuscleBatch(self.specs if len(self.specs) > 1 else self.specs[0], agents, device,
+                                 precision, fresh_outputs=False)
+        self.agents, self.S = int(agents), len(self.specs)
+        self.device, self.dtype = self.batch.device, self.batch.dtype
+        self.rest = None
+        if rest_lengths is not None:
+            self.rest = torch.as_tensor(rest_lengths, dtype=self.dtype, device=self.device).expand(self.agents, self.S)
+        self._prev_len = None
+
+    def reset(self):
+        self.batch.reset()
+        self._prev_len = None
+
+    def step(self, actions: torch.Tensor, step_size: float, lengths: Optional[torch.Tensor] = None):
+        """actions [agents, S] in the muscles' input units (0..1 for StandardMuscle);
+        lengths [agents, S] current muscle lengths (needs ``rest_lengths``).
+        Returns (outputs [agents, S], fatigue [agents, S] float64)."""
+        a = actions.to(device=self.device, dtype=self.dtype).reshape(self.agents, self.S)
+        gain = None
+        if lengths is not None:
+            if self.rest is None:
+                raise ValueError("lengths given but the environment has no rest_lengths")
+            cur = lengths.to(device=self.device, dtype=self.dtype).reshape(self.agents, self.S)
+            prev = cur if self._prev_len is None else self._prev_len
+            gain = contractile_element_force_length_curve(self.rest, cur) * \
+                contractile_element_force_velocity_curve(self.rest, cur, prev, step_size)
+            self._prev_len = cur.clone()
+        out, fat = self.batch.step_env(a, step_size, gain=gain, want_fatigue=True)
+        return out.view(self.agents, self.S), fat.view(self.agents, self.S)

@@ -269,6 +269,18 @@ def tables(pm):
     return out
 
 
+def hill(pm):
+    """Hill-type helper curves (pymuscle/hill_type.py) on random lengths."""
+    from pymuscle import hill_type as h
+    rng = np.random.default_rng(1)
+    rest = 0.5 + rng.random(64)
+    cur = rest * (0.7 + 0.8 * rng.random(64))
+    prev = cur * (0.95 + 0.1 * rng.random(64))
+    return dict(rest=rest, cur=cur, prev=prev, dt=0.02,
+                fl=h.contractile_element_force_length_curve(rest, cur),
+                fv=h.contractile_element_force_velocity_curve(rest, cur, prev, 0.02))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--check", action="store_true", help="compare oracle with the live reference bit for bit")
@@ -297,6 +309,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "arm.npz"), **arm(pm))
     np.savez_compressed(os.path.join(HERE, "tables.npz"), **tables(pm))
     np.savez_compressed(os.path.join(HERE, "readme_exact.npz"), **readme_exact(pm))
+    np.savez_compressed(os.path.join(HERE, "hill.npz"), **hill(pm))
     print("numpy", np.__version__)
     return 0
 

@@ -1,0 +1,89 @@
+"""
+The vector-environment step (mb_step_env through MuscleBatch.step_env / MuscleGroupEnv):
+outputs, Hill-type scaling and the fused peripheral-fatigue readout against the oracle's
+per-muscle loop -- the reference's `[muscle.step(a[i], dt) for i, muscle in enumerate(muscles)]`
+(examples/envs/muscled_hopper.py:33-34) followed by get_peripheral_fatigue (muscle.py:248-256).
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+from oracle.pymuscle_oracle import OracleMuscles
+from pymuscle_b200 import MuscleBatch, MuscleGroupEnv, MuscleSpec
+from test_gpu_parity import close
+
+pytestmark = pytest.mark.gpu
+
+FORCES = [48.0, 48.5, 35.0, 21.0]          # a hopper-like leg: four muscles of different size
+
+
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_env_step_matches_the_per_muscle_loop(cuda_device, precision):
+    specs = [MuscleSpec.standard(f) for f in FORCES]
+    agents, dt, frames = 37, 0.02, 25
+    env = MuscleGroupEnv(specs, agents, cuda_device, precision)
+    oras = [OracleMuscles.standard(f, m=agents) for f in FORCES]
+    rng = np.random.default_rng(11)
+    for k in range(frames):
+        a = rng.random((agents, len(specs))).astype(np.float32)
+        out, fat = env.step(torch.from_numpy(a), dt)
+        for s, o in enumerate(oras):
+            want = o.step(a[:, s].astype(np.float64), dt)
+            close(out[:, s].cpu().numpy(), want.total, precision, 1.0, f"outputs, muscle {s}, frame {k}")
+            close(fat[:, s].cpu().numpy(), o.peripheral_fatigue(), precision, 1.0, f"fatigue, muscle {s}, frame {k}")
+    assert fat.dtype == torch.float64 and bool((fat >= 0).all()) and bool((fat < 1).all())
+
+
+def test_env_step_is_one_launch_and_equals_step_plus_fatigue(cuda_device):
+    """The fused epilogue gives the same numbers as the two-kernel path, in one launch."""
+    g = golden("arm")
+    specs = [MuscleSpec.standard(max_force=float(f)) for f in g["max_forces"]]
+    a = MuscleBatch(specs, 16, cuda_device, "f32", fresh_outputs=False)
+    b = MuscleBatch(specs, 16, cuda_device, "f32", fresh_outputs=False)
+    x = torch.rand(16, 30, device=cuda_device)
+    for _ in range(5):
+        n0 = a.launches
+        out, fat = a.step_env(x, 0.02)
+        assert a.launches == n0 + 1
+        want = b.step(x, 0.02)
+        assert torch.equal(out, want)
+        np.testing.assert_allclose(fat.cpu().numpy(), b.get_peripheral_fatigue().cpu().numpy(), rtol=0, atol=2e-7)
+    assert torch.equal(a.cpf, b.cpf)
+
+
+def test_hill_type_gain_scales_the_outputs(cuda_device):
+    spec = MuscleSpec.standard()
+    agents = 64
+    rest = torch.full((1,), 0.3)
+    plain = MuscleGroupEnv(spec, agents, cuda_device, "f32")
+    hill = MuscleGroupEnv(spec, agents, cuda_device, "f32", rest_lengths=rest)
+    from pymuscle_b200 import (contractile_element_force_length_curve as fl_curve,
+                               contractile_element_force_velocity_curve as fv_curve)
+    rng = np.random.default_rng(2)
+    prev = None
+    for k in range(6):
+        act = torch.from_numpy(rng.random((agents, 1)).astype(np.float32))
+        cur = torch.from_numpy((0.3 * (0.8 + 0.5 * rng.random((agents, 1)))).astype(np.float32))
+        o0, f0 = plain.step(act, 0.02)
+        o1, f1 = hill.step(act, 0.02, lengths=cur)
+        p = cur if prev is None else prev
+        gain = fl_curve(0.3, cur.double().numpy()) * fv_curve(0.3, cur.double().numpy(), p.double().numpy(), 0.02)
+        # float32 evaluation of 1.8 - 1.8/(1 + e) cancels to 0 for fast lengthening: absolute term
+        np.testing.assert_allclose(o1.cpu().numpy(), o0.cpu().numpy() * gain, rtol=2e-6, atol=1e-6)
+        assert torch.equal(f0, f1)                             # the gain does not touch the fatigue state
+        prev = cur
+    with pytest.raises(ValueError):
+        plain.step(act, 0.02, lengths=cur)
+
+
+def test_env_step_falls_back_on_an_odd_row_length(cuda_device):
+    """L = 33 units: the streaming kernel declines, the generic kernels serve the same call."""
+    spec = MuscleSpec.potvin(33)
+    b = MuscleBatch(spec, 9, cuda_device, "f64")
+    o = OracleMuscles(33, 9, "potvin")
+    x = np.linspace(5.0, 60.0, 9)
+    out, fat = b.step_env(torch.from_numpy(x), 0.05)
+    close(out.cpu().numpy(), o.step(x, 0.05).total, "f64", 500.0, "totals")
+    want_f = np.array([1 - o.cpf[i].sum() / 1.0 for i in range(9)])           # potvin: divisor 1
+    np.testing.assert_allclose(fat.cpu().numpy(), want_f, rtol=1e-12)
