@@ -104,7 +104,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 // U-wide vector of T in shared memory (one LDS/STS of 4*U or 8*U bytes)
 template <typename T, int U> struct alignas(sizeof(T) * U) VecU { T v[U]; };
 
-__device__ __forceinline__ float2 bc(float x) { return make_float2(x, x); }   // broadcast operand of a packed op
 
 // ======================================================================================
 // Per-thread arithmetic of the two precision modes.  Each "core" holds the unit's
@@ -112,12 +111,15 @@ __device__ __forceinline__ float2 bc(float x) { return make_float2(x, x); }   //
 // ======================================================================================
 
 // ---- FP32 mode ------------------------------------------------------------------------
-// Instances are processed in pairs (x = instance 2p, y = instance 2p+1 of a float2).
+// Work is done on PAIRS: two unit-instances share one 64-bit register pair and the FMA-pipe
+// work is issued as packed FFMA2 / FMUL2 / FADD2.  A pair is either two muscles of the same
+// unit (parameters are scalars, broadcast operands: PT = float) or two units of the same
+// muscle (parameters are pairs: PT = float2).
 //
 // Capacity is carried as hi + lo (two floats): `hi` is frozen between renormalisations,
 // per-step decrements accumulate in the small `lo` (so their rounding error is relative to
 // the accumulated decrement, not to the capacity) and the pair is renormalised (error-free
-// TwoSum) every 4th tile.  On-duration is dur0 + count*dt with an exact float step
+// TwoSum) every 32 steps.  On-duration is dur0 + count*dt with an exact float step
 // counter.  Plain float accumulators miss rtol 1e-4 over 10,000 steps.
 //
 // CENTRAL: 0 = pool.apply_fatigue off (adaptation is the identity)
@@ -128,132 +130,218 @@ __device__ __forceinline__ float2 bc(float x) { return make_float2(x, x); }   //
 //              nD*decay + (decay - 1) -- and re-synchronised with one ex2 per tile from the
 //              exact counter, which replaces the per-step MUFU of the adaptation curve
 //          2 = on, general path with both clamps (pool:202-206, :221)
+__device__ __forceinline__ float2 B2(float v) { return make_float2(v, v); }
+__device__ __forceinline__ float2 B2(float2 v) { return v; }
+__device__ __forceinline__ float2 N2(float v) { return make_float2(-v, -v); }
+__device__ __forceinline__ float2 N2(float2 v) { return make_float2(-v.x, -v.y); }
+__device__ __forceinline__ float LX(float v) { return v; }
+__device__ __forceinline__ float LX(float2 v) { return v.x; }
+__device__ __forceinline__ float LY(float v) { return v; }
+__device__ __forceinline__ float LY(float2 v) { return v.y; }
+
+template <typename PT>
+struct PairParams {            // what a step needs of the unit(s) of a pair
+    PT crit, thr_g, peak, phir, phir6, ctA, ctB, fatdt, rdidt, ptf, ptf_lo;
+};
+struct PairState {
+    float2 hi, lo, cpf, cnt, nD, room, arg0;
+};
+struct PairScal {              // per-launch scalars
+    float gain_e, c25k, ythr, argmin, dtk, decay, dm1;
+};
+
+__device__ __forceinline__ float& el(float2& v, int k) { return k ? v.y : v.x; }
+
+template <typename PT>
+__device__ __forceinline__ void pair_init(PairState& st, const PairParams<PT>& p, int k, double c, double d0, double adk_d) {
+    const float h = (float)c;
+    const float l = (float)(c - (double)h);
+    const float ptf = k ? LY(p.ptf) : LX(p.ptf), ptf_lo = k ? LY(p.ptf_lo) : LX(p.ptf_lo);
+    el(st.hi, k) = h;
+    el(st.lo, k) = l;
+    el(st.cpf, k) = h + l;
+    el(st.room, k) = (ptf - h) + ptf_lo;                 // peak - hi: the upper bound of lo (pmf:104-105)
+    el(st.cnt, k) = 0.0f;
+    el(st.nD, k) = 0.0f;
+    el(st.arg0, k) = (float)(d0 * adk_d);
+}
+
+template <int CENTRAL>
+__device__ __forceinline__ void pair_begin_tile(PairState& st, const PairScal& sc) {
+    if (CENTRAL == 1) {
+        st.nD.x = ex2_approx(fmaf(st.cnt.x, sc.dtk, st.arg0.x)) - 1.0f;
+        st.nD.y = ex2_approx(fmaf(st.cnt.y, sc.dtk, st.arg0.y)) - 1.0f;
+    }
+}
+
+// One step of a pair; x = the two excitations; returns the two unit forces.
+// Without adaptation in the loop (CENTRAL != 1) recruitment enters the arithmetic as a float
+// mask onf (1 = recruited): the firing rate is multiplied by it and the recovery term is blended
+// with it, so the FMA-pipe work stays packed and the only scalar (ALU-pipe) instructions are the
+// two compares, the peak clamp, the curve select and the capacity clamp.
+template <int FIB, int CENTRAL, typename PT>
+__device__ __forceinline__ float2 pair_step(PairState& st, const PairParams<PT>& p, const PairScal& sc, float2 x,
+                                            bool& on_a, bool& on_b) {
+    // ---- pool: rate and recruitment (pool:150-179) ----
+    float2 r = __ffma2_rn(x, B2(sc.gain_e), N2(p.thr_g));
+    float2 onf;
+    onf.x = (x.x >= LX(p.crit)) ? 1.0f : 0.0f;                              // pool:171 (exact mask: see mb_params_pack)
+    onf.y = (x.y >= LY(p.crit)) ? 1.0f : 0.0f;
+    r.x = fminf(r.x, LX(p.peak));
+    r.y = fminf(r.y, LY(p.peak));
+    float2 fr;
+    if (CENTRAL == 0) {
+        fr = __fmul2_rn(r, onf);                                            // pool:172
+    } else if (CENTRAL == 1) {
+        // measured on B200: with the adaptation recurrences in the loop the FMA pipe is the busiest
+        // unit, so here the recruitment mask is used as a predicate (scalar, predicated updates)
+        // rather than blended arithmetically (which costs two more FMA-pipe operations per step)
+        const float2 q = __ffma2_rn(r, B2(p.phir), N2(p.phir6));            // pool:231-232
+        fr = __ffma2_rn(q, st.nD, r);                                       // r - q*(1 - exp(-dur/tau)), dur BEFORE the update
+        const bool oa = x.x >= LX(p.crit), ob = x.y >= LY(p.crit);
+        fr.x = oa ? fr.x : 0.0f;                                            // pool:171-172
+        fr.y = ob ? fr.y : 0.0f;
+        if (oa) {                                                           // pool:196-197
+            st.cnt.x += 1.0f;
+            st.nD.x = fmaf(st.nD.x, sc.decay, sc.dm1);
+        }
+        if (ob) {
+            st.cnt.y += 1.0f;
+            st.nD.y = fmaf(st.nD.y, sc.decay, sc.dm1);
+        }
+    } else {
+        const bool oa = onf.x != 0.0f, ob = onf.y != 0.0f;
+        const float2 arg = __ffma2_rn(st.cnt, B2(sc.dtk), st.arg0);
+        st.cnt = __fadd2_rn(st.cnt, onf);
+        const float ra = oa ? r.x : 0.0f, rb = ob ? r.y : 0.0f;
+        const float qa = fmaf(ra, LX(p.phir), -LX(p.phir6)), qb = fmaf(rb, LY(p.phir), -LY(p.phir6));
+        const float aa = fmaf(-qa, ex2_approx(fmaxf(arg.x, sc.argmin)), qa);            // pool:217-219
+        const float ab = fmaf(-qb, ex2_approx(fmaxf(arg.y, sc.argmin)), qb);
+        fr.x = ra - fmaxf(aa, 0.0f);                                        // pool:221, :121
+        fr.y = rb - fmaxf(ab, 0.0f);
+    }
+    on_a = onf.x != 0.0f;
+    on_b = onf.y != 0.0f;
+    // ---- fibers (fibers:211-259) on ny = -kappa*x: exp(-2x^3) = ex2(ny^3) ----
+    const float2 ctkn = __ffma2_rn(st.cpf, B2(p.ctB), N2(p.ctA));           // -kappa*ct_cur/1000
+    const float2 ny = __fmul2_rn(ctkn, fr);
+    const float2 lin = __fmul2_rn(ny, B2(-sc.c25k));
+    const float2 y2 = __fmul2_rn(ny, ny);
+    const float2 ny3 = __fmul2_rn(y2, ny);
+    float2 ex;
+    ex.x = ex2_approx(ny3.x);
+    ex.y = ex2_approx(ny3.y);
+    const float2 sig = __ffma2_rn(ex, B2(-1.0f), B2(1.0f));
+    float2 nf;
+    nf.x = (ny.x >= -sc.ythr) ? lin.x : sig.x;                              // x <= 0.4 (fibers:233-236)
+    nf.y = (ny.y >= -sc.ythr) ? lin.y : sig.y;
+    const float2 F = __fmul2_rn(nf, st.cpf);                                // fibers:258 (capacity BEFORE the update)
+    // ---- capacity update on the compensated pair (fibers:110-114, pmf:94-105) ----
+    float2 l = __ffma2_rn(nf, N2(p.fatdt), st.lo);
+    if (FIB == MB_FIBERS_PYMUSCLE) {
+        // recovery of a unit that does not fire (nf <= 0  <=>  not recruited):
+        // l += (peak - capacity) * (1 - onf) * rdidt                        pmf:121-141
+        float2 firing = onf;
+        if (CENTRAL == 2) {                                                 // general parameters: test nf itself
+            firing.x = (nf.x > 0.0f) ? 1.0f : 0.0f;
+            firing.y = (nf.y > 0.0f) ? 1.0f : 0.0f;
+        }
+        const float2 gap = __fadd2_rn(st.room, N2(st.lo));
+        const float2 gn = __ffma2_rn(gap, N2(firing), gap);
+        l = __ffma2_rn(gn, B2(p.rdidt), l);
+    }
+    l.x = fmaxf(l.x, -st.hi.x);                                             // fibers:114
+    l.y = fmaxf(l.y, -st.hi.y);
+    // (the upper clamp at the peak, pmf:104-105, is applied in pair_renormalise(): recovery approaches
+    //  the peak from below and can overshoot it only by rounding)
+    st.lo = l;
+    st.cpf = __fadd2_rn(st.hi, l);
+    return F;
+}
+
+// renormalise (TwoSum) so that |lo| <= ulp(hi)/2 again; applies the upper clamp of PyMuscle fibers
+template <int FIB, typename PT>
+__device__ __forceinline__ void pair_renormalise(PairState& st, const PairParams<PT>& p) {
+    if (FIB == MB_FIBERS_PYMUSCLE) {                                        // pmf:104-105
+        st.lo.x = fminf(st.lo.x, st.room.x);
+        st.lo.y = fminf(st.lo.y, st.room.y);
+    }
+    const float2 s1 = __fadd2_rn(st.hi, st.lo);
+    const float2 bb = __fadd2_rn(s1, N2(st.hi));
+    const float2 t1 = __fadd2_rn(s1, N2(bb));
+    const float2 e1 = __fadd2_rn(st.hi, N2(t1));
+    const float2 e2 = __fadd2_rn(st.lo, N2(bb));
+    st.hi = s1;
+    st.lo = __fadd2_rn(e1, e2);
+    st.room = __fadd2_rn(__fadd2_rn(B2(p.ptf), N2(s1)), B2(p.ptf_lo));
+}
+
+// write element k of a pair back to the float64 state
+template <bool CENTRAL>
+__device__ __forceinline__ void pair_store(PairState& st, int k, const K2Args& a, int64_t idx) {
+    if (a.peripheral) {
+        // add the window's change to the float64 state: an untouched unit keeps its
+        // exact bits, and the low bits of the incoming capacity are not truncated
+        const double c0 = a.cpf[idx];
+        const float h0 = (float)c0;
+        const float l0 = (float)(c0 - (double)h0);
+        a.cpf[idx] = c0 + (((double)el(st.hi, k) - (double)h0) + ((double)el(st.lo, k) - (double)l0));
+    }
+    if (CENTRAL) {
+        double d = fma((double)el(st.cnt, k), a.dt, a.dur[idx]);
+        d = (d > a.max_dur) ? a.max_dur : d;
+        a.dur[idx] = (d < 0.0) ? 0.0 : d;
+    }
+}
+
+__device__ __forceinline__ PairScal pair_scal(const K2Args& a) {
+    PairScal s;
+    s.gain_e = a.sf.gain_e; s.c25k = a.sf.c25k; s.ythr = a.sf.ythr; s.argmin = a.sf.argmin;
+    s.dtk = a.dtk; s.decay = a.decay; s.dm1 = a.dm1;
+    return s;
+}
+__device__ __forceinline__ PairParams<float> pair_params(const UnitF& u, const K2Args& a) {
+    PairParams<float> p;
+    p.crit = u.crit; p.thr_g = u.thr_g; p.peak = u.peak; p.phir = u.phir; p.phir6 = u.phir6;
+    p.ctA = u.ctA; p.ctB = u.ctB; p.ptf = u.ptf; p.ptf_lo = u.ptf_lo;
+    p.fatdt = a.peripheral ? (float)((double)u.fat * a.dt) : 0.0f;
+    p.rdidt = a.peripheral ? (float)((double)u.rdi * a.dt) : 0.0f;
+    return p;
+}
+
+// U instances (muscles) of ONE unit: pairs of muscles, scalar parameters
 template <int FIB, int CENTRAL, int U>
 struct CoreF32 {
     using T = float;
     using V = VecU<float, U>;
     static constexpr bool kCentral = CENTRAL != 0;
     static constexpr int NP = (U + 1) / 2;           // pairs
-    UnitF p;
-    ScalF sc;
-    float fatdt, rdidt, dtk, decay, dm1;
-    float2 hi[NP], lo[NP], cpf[NP], cnt[NP], nD[NP], room[NP];
-    float arg0[2 * NP];
+    UnitF u;
+    PairParams<float> p;
+    PairScal sc;
+    float inv_out;
+    PairState st[NP];
 
-    static __device__ __forceinline__ float& el(float2& v, int k) { return k ? v.y : v.x; }
-
-    __device__ __forceinline__ void load(const K2Args& a, int u) {
-        p = load_unit((const float4*)a.params, a.n, u);
-        sc = a.sf;
-        fatdt = a.peripheral ? (float)((double)p.fat * a.dt) : 0.0f;
-        rdidt = a.peripheral ? (float)((double)p.rdi * a.dt) : 0.0f;
-        dtk = a.dtk;
-        decay = a.decay;
-        dm1 = a.dm1;
+    __device__ __forceinline__ void load(const K2Args& a, int unit) {
+        u = load_unit((const float4*)a.params, a.n, unit);
+        p = pair_params(u, a);
+        sc = pair_scal(a);
+        inv_out = a.sf.inv_out;
 #pragma unroll
         for (int j = 0; j < 2 * NP; ++j) init(j, a, rest_capacity(), 0.0);   // the idle half of an odd U
     }
-    __device__ __forceinline__ double rest_capacity() const { return unit_peak(p); }
+    __device__ __forceinline__ void disable() { p.crit = __int_as_float(0x7f800000); }   // never recruited, force 0
+    __device__ __forceinline__ double rest_capacity() const { return unit_peak(u); }
     __device__ __forceinline__ void init(int j, const K2Args& a, double c, double d0) {
-        const int pi = j >> 1, k = j & 1;
-        const float h = (float)c;
-        const float l = (float)(c - (double)h);
-        el(hi[pi], k) = h;
-        el(lo[pi], k) = l;
-        el(cpf[pi], k) = h + l;
-        el(room[pi], k) = (p.ptf - h) + p.ptf_lo;        // peak - hi: the upper bound of lo (pmf:104-105)
-        el(cnt[pi], k) = 0.0f;
-        el(nD[pi], k) = 0.0f;
-        arg0[j] = (float)(d0 * a.adk_d);
+        pair_init(st[j >> 1], p, j & 1, c, d0, a.adk_d);
     }
     __device__ __forceinline__ void begin_tile() {
-        if (CENTRAL == 1) {
 #pragma unroll
-            for (int j = 0; j < 2 * NP; ++j)
-                el(nD[j >> 1], j & 1) = ex2_approx(fmaf(el(cnt[j >> 1], j & 1), dtk, arg0[j])) - 1.0f;
-        }
+        for (int pi = 0; pi < NP; ++pi) pair_begin_tile<CENTRAL>(st[pi], sc);
     }
-
-    // one step of the pair pi; x = the two excitations; returns the two unit forces.
-    // Recruitment enters the arithmetic as a float mask onf (1 = recruited): the firing rate is
-    // multiplied by it and the counter / adaptation recurrences are blended with it, so the FMA-pipe
-    // work stays packed and the only scalar (ALU-pipe) instructions are the two compares, the peak
-    // clamp, the curve select and the capacity clamp.
     __device__ __forceinline__ float2 step_pair(int pi, float2 x, bool& on_a, bool& on_b) {
-        // ---- pool: rate and recruitment (pool:150-179) ----
-        float2 r = __ffma2_rn(x, bc(sc.gain_e), bc(-p.thr_g));
-        float2 onf;
-        onf.x = (x.x >= p.crit) ? 1.0f : 0.0f;                              // pool:171 (exact mask: see mb_params_pack)
-        onf.y = (x.y >= p.crit) ? 1.0f : 0.0f;
-        r.x = fminf(r.x, p.peak);
-        r.y = fminf(r.y, p.peak);
-        float2 fr;
-        if (CENTRAL == 0) {
-            fr = __fmul2_rn(r, onf);                                        // pool:172
-        } else if (CENTRAL == 1) {
-            // measured on B200: with the adaptation recurrences in the loop the FMA pipe is the busiest
-            // unit, so here the recruitment mask is used as a predicate (scalar, predicated updates)
-            // rather than blended arithmetically (which costs two more FMA-pipe operations per step)
-            const float2 q = __ffma2_rn(r, bc(p.phir), bc(-p.phir6));       // pool:231-232
-            fr = __ffma2_rn(q, nD[pi], r);                                  // r - q*(1 - exp(-dur/tau)), dur BEFORE the update
-            const bool oa = x.x >= p.crit, ob = x.y >= p.crit;
-            fr.x = oa ? fr.x : 0.0f;                                        // pool:171-172
-            fr.y = ob ? fr.y : 0.0f;
-            if (oa) {                                                       // pool:196-197
-                cnt[pi].x += 1.0f;
-                nD[pi].x = fmaf(nD[pi].x, decay, dm1);
-            }
-            if (ob) {
-                cnt[pi].y += 1.0f;
-                nD[pi].y = fmaf(nD[pi].y, decay, dm1);
-            }
-        } else {
-            const bool oa = onf.x != 0.0f, ob = onf.y != 0.0f;
-            float2 arg = __ffma2_rn(cnt[pi], bc(dtk), make_float2(arg0[2 * pi], arg0[2 * pi + 1]));
-            cnt[pi] = __fadd2_rn(cnt[pi], onf);
-            const float ra = oa ? r.x : 0.0f, rb = ob ? r.y : 0.0f;
-            fr.x = ra - fmaxf(pool_adaptation(p, ra, fmaxf(arg.x, sc.argmin)), 0.0f);
-            fr.y = rb - fmaxf(pool_adaptation(p, rb, fmaxf(arg.y, sc.argmin)), 0.0f);
-        }
-        on_a = onf.x != 0.0f;
-        on_b = onf.y != 0.0f;
-        // ---- fibers (fibers:211-259) on ny = -kappa*x: exp(-2x^3) = ex2(ny^3) ----
-        const float2 ctkn = __ffma2_rn(cpf[pi], bc(p.ctB), bc(-p.ctA));     // -kappa*ct_cur/1000
-        const float2 ny = __fmul2_rn(ctkn, fr);
-        const float2 lin = __fmul2_rn(ny, bc(-sc.c25k));
-        const float2 y2 = __fmul2_rn(ny, ny);
-        const float2 ny3 = __fmul2_rn(y2, ny);
-        float2 ex;
-        ex.x = ex2_approx(ny3.x);
-        ex.y = ex2_approx(ny3.y);
-        const float2 sig = __ffma2_rn(ex, bc(-1.0f), bc(1.0f));
-        float2 nf;
-        nf.x = (ny.x >= -sc.ythr) ? lin.x : sig.x;                          // x <= 0.4 (fibers:233-236)
-        nf.y = (ny.y >= -sc.ythr) ? lin.y : sig.y;
-        const float2 F = __fmul2_rn(nf, cpf[pi]);                           // fibers:258 (capacity BEFORE the update)
-        // ---- capacity update on the compensated pair (fibers:110-114, pmf:94-105) ----
-        float2 l = __ffma2_rn(nf, bc(-fatdt), lo[pi]);
-        if (FIB == MB_FIBERS_PYMUSCLE) {
-            // recovery of a unit that does not fire (nf <= 0  <=>  not recruited):
-            // l += (peak - capacity) * (1 - onf) * rdidt                    pmf:121-141
-            float2 firing = onf;
-            if (CENTRAL == 2) {                                             // general parameters: test nf itself
-                firing.x = (nf.x > 0.0f) ? 1.0f : 0.0f;
-                firing.y = (nf.y > 0.0f) ? 1.0f : 0.0f;
-            }
-            const float2 gap = __fadd2_rn(room[pi], make_float2(-lo[pi].x, -lo[pi].y));
-            const float2 gn = __ffma2_rn(gap, make_float2(-firing.x, -firing.y), gap);
-            l = __ffma2_rn(gn, bc(rdidt), l);
-        }
-        l.x = fmaxf(l.x, -hi[pi].x);                                        // fibers:114
-        l.y = fmaxf(l.y, -hi[pi].y);
-        // (the upper clamp at the peak, pmf:104-105, is applied in renormalise(): recovery approaches the
-        //  peak from below and can overshoot it only by rounding)
-        lo[pi] = l;
-        cpf[pi] = __fadd2_rn(hi[pi], l);
-        return F;
+        return pair_step<FIB, CENTRAL>(st[pi], p, sc, x, on_a, on_b);
     }
-
     // one step of all U instances: e -> f (forces); onbits = recruitment mask of the instances
     __device__ __forceinline__ void step_vec(const V& e, V& f, unsigned& onbits) {
         onbits = 0;
@@ -268,43 +356,15 @@ struct CoreF32 {
             if (2 * pi + 1 < U) onbits |= (ob ? 1u : 0u) << j1;
         }
     }
-
     __device__ __forceinline__ void set_table(const double*) {}
-    // renormalise (TwoSum) so that |lo| <= ulp(hi)/2 again
     __device__ __forceinline__ void renormalise() {
 #pragma unroll
-        for (int pi = 0; pi < NP; ++pi) {
-            if (FIB == MB_FIBERS_PYMUSCLE) {                                // pmf:104-105
-                lo[pi].x = fminf(lo[pi].x, room[pi].x);
-                lo[pi].y = fminf(lo[pi].y, room[pi].y);
-            }
-            const float2 s1 = __fadd2_rn(hi[pi], lo[pi]);
-            const float2 bb = __fadd2_rn(s1, make_float2(-hi[pi].x, -hi[pi].y));
-            const float2 t1 = __fadd2_rn(s1, make_float2(-bb.x, -bb.y));
-            const float2 e1 = __fadd2_rn(hi[pi], make_float2(-t1.x, -t1.y));
-            const float2 e2 = __fadd2_rn(lo[pi], make_float2(-bb.x, -bb.y));
-            hi[pi] = s1;
-            lo[pi] = __fadd2_rn(e1, e2);
-            room[pi] = __fadd2_rn(__fadd2_rn(bc(p.ptf), make_float2(-s1.x, -s1.y)), bc(p.ptf_lo));
-        }
+        for (int pi = 0; pi < NP; ++pi) pair_renormalise<FIB>(st[pi], p);
     }
     __device__ __forceinline__ void store(int j, const K2Args& a, int64_t idx) {
-        const int pi = j >> 1, k = j & 1;
-        if (a.peripheral) {
-            // add the window's change to the float64 state: an untouched unit keeps its
-            // exact bits, and the low bits of the incoming capacity are not truncated
-            const double c0 = a.cpf[idx];
-            const float h0 = (float)c0;
-            const float l0 = (float)(c0 - (double)h0);
-            a.cpf[idx] = c0 + (((double)el(hi[pi], k) - (double)h0) + ((double)el(lo[pi], k) - (double)l0));
-        }
-        if (CENTRAL) {
-            double d = fma((double)el(cnt[pi], k), a.dt, a.dur[idx]);
-            d = (d > a.max_dur) ? a.max_dur : d;
-            a.dur[idx] = (d < 0.0) ? 0.0 : d;
-        }
+        pair_store<CENTRAL != 0>(st[j >> 1], j & 1, a, idx);
     }
-    __device__ __forceinline__ float out_scale(float v) const { return v * sc.inv_out; }
+    __device__ __forceinline__ float out_scale(float v) const { return v * inv_out; }
 };
 
 // ---- FP64 mode ------------------------------------------------------------------------

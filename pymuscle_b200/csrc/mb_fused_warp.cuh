@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MB_W_MINB) k2w_f32(const 
         const int u = lane + 32 * i;
         const bool valid = u < n;
         core[i].load(a, valid ? u : 0);
-        if (!valid) core[i].p.crit = __int_as_float(0x7f800000);        // idle slot: never recruited, force 0
+        if (!valid) core[i].disable();                                  // idle slot: never recruited, force 0
         if (valid) {
             core[i].init(0, a, a.cpf[m0 * n + u], CENTRAL ? a.dur[m0 * n + u] : 0.0);
             if (two) core[i].init(1, a, a.cpf[(m0 + 1) * n + u], CENTRAL ? a.dur[(m0 + 1) * n + u] : 0.0);
