@@ -39,6 +39,7 @@ struct K1sArgs {
     const typename StreamTraits<T>::P* params;
     int64_t rows, L;
     int32_t S, W, NS;
+    int32_t seg_in_smem;         // 1: seg_off / seg_div are copied to shared memory at kernel start
     const int32_t* seg_off;
     const double* seg_div;
     int32_t peripheral;
@@ -97,6 +98,19 @@ __global__ void __launch_bounds__(288, 2) k1_stream(const K1sArgs<T> a) {
     double* cpf_s = (double*)(smem_raw + 128);            // [NS][R][rowp]
     double* dur_s = cpf_s + (size_t)NS * R * rowp;        // [NS][R][rowp]   (CENTRAL only)
     T* red = (T*)(CENTRAL ? dur_s + (size_t)NS * R * rowp : dur_s);   // [2R][8]: force sums | capacity sums
+    // ragged rows: segment offsets and divisors are read once per work item by every thread ->
+    // keep them in shared memory instead of paying a dependent global load per item
+    double* segdiv_s = (double*)(red + 2 * R * 8);        // [S]
+    int32_t* segoff_s = (int32_t*)(segdiv_s + (a.seg_in_smem ? a.S : 0));   // [S + 1]
+    const int32_t* seg_off = a.seg_off;
+    const double* seg_div = a.seg_div;
+    if (a.seg_in_smem) {
+        for (int i = threadIdx.x; i <= a.S; i += blockDim.x) segoff_s[i] = a.seg_off[i];
+        if (a.seg_div)
+            for (int i = threadIdx.x; i < a.S; i += blockDim.x) segdiv_s[i] = a.seg_div[i];
+        seg_off = segoff_s;
+        if (a.seg_div) seg_div = segdiv_s;
+    }
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ncons = blockDim.x - 32;                    // consumer threads (== W)
@@ -120,8 +134,8 @@ __global__ void __launch_bounds__(288, 2) k1_stream(const K1sArgs<T> a) {
             const int64_t chunk = item / a.S;
             const int seg = (int)(item - chunk * a.S);
             const int64_t r0 = chunk * R;
-            const int off0 = a.seg_off ? a.seg_off[seg] : 0;
-            const int n = a.seg_off ? a.seg_off[seg + 1] - off0 : (int)a.L;
+            const int off0 = seg_off ? seg_off[seg] : 0;
+            const int n = seg_off ? seg_off[seg + 1] - off0 : (int)a.L;
             const int nrows = (int)min((int64_t)R, a.rows - r0);
             for (int u0 = 0; u0 < n; u0 += W, ++it) {
                 const uint32_t s = it % NS, ph = (it / NS) & 1;
@@ -159,8 +173,8 @@ __global__ void __launch_bounds__(288, 2) k1_stream(const K1sArgs<T> a) {
         const int64_t chunk = item / a.S;
         const int seg = (int)(item - chunk * a.S);
         const int64_t r0 = chunk * R;
-        const int off0 = a.seg_off ? a.seg_off[seg] : 0;
-        const int n = a.seg_off ? a.seg_off[seg + 1] - off0 : (int)a.L;
+        const int off0 = seg_off ? seg_off[seg] : 0;
+        const int n = seg_off ? seg_off[seg + 1] - off0 : (int)a.L;
         const int nrows = (int)min((int64_t)R, a.rows - r0);
         T xm[R], partial[R], csum[R];
 #pragma unroll
@@ -236,13 +250,13 @@ __global__ void __launch_bounds__(288, 2) k1_stream(const K1sArgs<T> a) {
                 if (a.totals) {
                     T sum = red[tid * 8];
                     for (int w = 1; w < ncw; ++w) sum += red[tid * 8 + w];
-                    sum = a.seg_div ? out_div(sum, a.seg_div[seg]) : out_scale(a.sc, sum);
+                    sum = seg_div ? out_div(sum, seg_div[seg]) : out_scale(a.sc, sum);
                     a.totals[mu] = a.out_gain ? sum * a.out_gain[mu] : sum;      // epilogue: Hill-type factors etc.
                 }
                 if (want_fatigue) {
                     double cs = (double)red[(R + tid) * 8];
                     for (int w = 1; w < ncw; ++w) cs += (double)red[(R + tid) * 8 + w];
-                    a.fatigue[mu] = 1.0 - cs / (a.seg_div ? a.seg_div[seg] : a.fat_div);
+                    a.fatigue[mu] = 1.0 - cs / (seg_div ? seg_div[seg] : a.fat_div);
                 }
             }
             asm volatile("bar.sync 1, %0;" ::"r"(ncons) : "memory");
