@@ -170,6 +170,27 @@ int mb_step_fused(const MbConfig* cfg, const void* params_dev,
                   void* forces_last_dev,
                   double step_size, int32_t units_per_thread /* 0 = auto */, void* stream);
 
+/* ---- K2 with the gather of totals fused into its epilogue (multi-GPU) -----------------------
+ * Same as mb_step_fused, but every per-(step, muscle) total is also stored into `n_peers` further
+ * buffers -- in practice the gather buffers of the other GPUs of the box, mapped into this
+ * process (CUDA IPC / symmetric memory) -- with plain stores that travel over NVLink while the
+ * kernel keeps computing.  The local copy uses totals_stride_k; in a peer buffer element
+ * (step k, local muscle m) lives at (m >> 1) * peer_stride_pair + k * peer_stride_k + (m & 1):
+ * (stride_k, stride_pair) = (M_total, 2) is the ordinary [K, M] layout, (2, 2 * K_max) the
+ * pair-major layout in which a warp's stores of a 32-step tile are 256 contiguous bytes.  The
+ * caller passes pointers that already include this rank's region offset and synchronises the
+ * ranks afterwards (a barrier) before anyone reads.  The reference has no counterpart
+ * (single process); it replaces an all_gather after the window.  `peer_totals_dev` is a HOST
+ * array of device pointers, n_peers <= 8. */
+int mb_step_fused_gather(const MbConfig* cfg, const void* params_dev,
+                         int64_t M, int32_t n, int32_t K,
+                         const void* exc_dev, int64_t exc_stride_k,
+                         double* cpf_dev, double* dur_dev,
+                         void* totals_dev, int64_t totals_stride_k,
+                         void* const* peer_totals_dev, int32_t n_peers,
+                         int64_t peer_stride_k, int64_t peer_stride_pair,
+                         void* forces_last_dev, double step_size, void* stream);
+
 /* Launch geometry mb_step_fused would use (for reporting): muscles per block,
  * threads per block, blocks, dynamic shared memory bytes. */
 int mb_fused_geometry(const MbConfig* cfg, int64_t M, int32_t n, int32_t K, int32_t units_per_thread,

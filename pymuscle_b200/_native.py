@@ -24,7 +24,7 @@ MB_PROP_ADAPT_NONNEG = 1
 #: every symbol include/muscle_b200.h declares (tests check the .so exports them all)
 SYMBOLS = (
     "mb_abi_version", "mb_last_error", "mb_params_bytes", "mb_params_pack", "mb_step", "mb_step_env",
-    "mb_step_fused", "mb_fused_geometry", "mb_peripheral_fatigue", "mb_peak_probe",
+    "mb_step_fused", "mb_step_fused_gather", "mb_fused_geometry", "mb_peripheral_fatigue", "mb_peak_probe",
 )
 
 
@@ -82,6 +82,9 @@ def _declare(lib):
     lib.mb_step_env.argtypes = [cfgp, vp, i64, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, dbl, vp]
     lib.mb_step_fused.restype = C.c_int
     lib.mb_step_fused.argtypes = [cfgp, vp, i64, i32, i32, vp, i64, vp, vp, vp, i64, vp, vp, i32, vp, dbl, i32, vp]
+    lib.mb_step_fused_gather.restype = C.c_int
+    lib.mb_step_fused_gather.argtypes = [cfgp, vp, i64, i32, i32, vp, i64, vp, vp, vp, i64, C.POINTER(vp), i32,
+                                         i64, i64, vp, dbl, vp]
     lib.mb_fused_geometry.restype = C.c_int
     lib.mb_fused_geometry.argtypes = [cfgp, i64, i32, i32, i32, C.POINTER(i32), C.POINTER(i32),
                                       C.POINTER(i64), C.POINTER(i32)]

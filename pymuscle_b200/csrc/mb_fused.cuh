@@ -37,6 +37,7 @@
 
 namespace mb {
 
+constexpr int kMaxPeers = 8;     // destinations of the fused totals gather besides `totals`
 constexpr int kExcSlots = 16;    // excitation ring (tiles)
 constexpr int kExcAhead = 6;     // tiles staged ahead of the staging warp's own position (> PT drift bound)
 constexpr int kPtSlots = 4;      // partial-sum ring (tiles)
@@ -54,6 +55,9 @@ struct K2Args {
     double* dur;
     void* totals;
     int64_t totals_stride_k;
+    void* totals_peer[kMaxPeers];  // further copies of the totals (same stride): peer GPUs' gather buffers, written
+    int32_t n_peers;               // straight from the kernel over NVLink (the all-gather fused into the epilogue)
+    int64_t peer_stride_k, peer_stride_pair;   // peer element (k, m) at (m >> 1)*stride_pair + k*stride_k + (m & 1)
     void* forces_dec;
     uint8_t* mask_dec;
     int32_t forces_every;
@@ -558,7 +562,16 @@ __device__ __forceinline__ void k2_body(const K2Args& a) {
                 T acc = src[0];
 #pragma unroll 5
                 for (int q2 = 1; q2 < a.npg; ++q2) acc += src[q2 * U];
-                if (g < gcount) totals[(int64_t)(k0 + s) * a.totals_stride_k + m0 + g] = core.out_scale(acc);
+                if (g < gcount) {
+                    const int64_t o = (int64_t)(k0 + s) * a.totals_stride_k + m0 + g;
+                    const T v = core.out_scale(acc);
+                    totals[o] = v;
+                    if (a.n_peers > 0) {                               // peer GPUs (NVLink stores)
+                        const int64_t mg = m0 + g;
+                        const int64_t op = (mg >> 1) * a.peer_stride_pair + (int64_t)(k0 + s) * a.peer_stride_k + (mg & 1);
+                        for (int pr = 0; pr < a.n_peers; ++pr) ((T*)a.totals_peer[pr])[op] = v;
+                    }
+                }
             }
         }
         __syncwarp();

@@ -134,9 +134,26 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MB_W_MINB) k2w_f32(const 
             }
             const float2 acc = __fadd2_rn(acc0, acc1);
             if (a.totals) {
-                float* t = (float*)a.totals + (int64_t)(k0 + lane) * a.totals_stride_k + m0;
-                t[0] = core[0].out_scale(acc.x);
-                if (two) t[1] = core[0].out_scale(acc.y);
+                const int64_t o = (int64_t)(k0 + lane) * a.totals_stride_k + m0;
+                const float t0 = core[0].out_scale(acc.x), t1 = core[0].out_scale(acc.y);
+                float* t = (float*)a.totals + o;
+                t[0] = t0;
+                if (two) t[1] = t1;
+                if (a.n_peers > 0) {
+                    // the same totals into the peer GPUs' gather buffers.  With the pair-major layout
+                    // (stride_k == 2) the 32 lanes of the warp write 256 contiguous bytes per tile
+                    const int64_t op = (m0 >> 1) * a.peer_stride_pair + (int64_t)(k0 + lane) * a.peer_stride_k;
+                    const bool vec = two && (((a.peer_stride_pair | a.peer_stride_k) & 1) == 0);
+                    for (int pr = 0; pr < a.n_peers; ++pr) {
+                        float* tp = (float*)a.totals_peer[pr] + op;
+                        if (vec) {
+                            *(float2*)tp = make_float2(t0, t1);
+                        } else {
+                            tp[0] = t0;
+                            if (two) tp[1] = t1;
+                        }
+                    }
+                }
             }
         }
         __syncwarp();

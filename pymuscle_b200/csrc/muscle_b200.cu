@@ -789,11 +789,12 @@ static int launch_fused(KernelT kernel, const K2Args& a, const FusedGeom& g, cud
 #define MB_DISPATCH_FIB64(UU)                                                                  \
     (fib == MB_FIBERS_POTVIN ? MB_DISPATCH_CENTRAL64(MB_FIBERS_POTVIN, UU) : MB_DISPATCH_CENTRAL64(MB_FIBERS_PYMUSCLE, UU))
 
-extern "C" int mb_step_fused(const MbConfig* cfg, const void* params_dev, int64_t M, int32_t n, int32_t K,
-                             const void* exc_dev, int64_t exc_stride_k, double* cpf_dev, double* dur_dev,
-                             void* totals_dev, int64_t totals_stride_k, void* forces_dec_dev, uint8_t* mask_dec_dev,
-                             int32_t forces_every, void* forces_last_dev, double step_size,
-                             int32_t units_per_thread, void* stream) {
+static int step_fused_impl(const MbConfig* cfg, const void* params_dev, int64_t M, int32_t n, int32_t K,
+                           const void* exc_dev, int64_t exc_stride_k, double* cpf_dev, double* dur_dev,
+                           void* totals_dev, int64_t totals_stride_k, void* forces_dec_dev, uint8_t* mask_dec_dev,
+                           int32_t forces_every, void* forces_last_dev, double step_size,
+                           int32_t units_per_thread, void* stream, void* const* peer_totals, int32_t n_peers,
+                           int64_t peer_stride_k, int64_t peer_stride_pair) {
     if (int rc = check_cfg(cfg)) return rc;
     if (!params_dev || !exc_dev || !cpf_dev) return fail(MB_EINVAL, "mb_step_fused: params/exc/cpf is NULL");
     if (cfg->central_fatigue && !dur_dev) return fail(MB_EINVAL, "mb_step_fused: dur is NULL");
@@ -819,6 +820,16 @@ extern "C" int mb_step_fused(const MbConfig* cfg, const void* params_dev, int64_
         a.exc_mode = (aligned && !env_int("MB_FUSED_NO_BULK", 0)) ? 0 : 1;
     }
     a.cpf = cpf_dev; a.dur = dur_dev; a.totals = totals_dev; a.totals_stride_k = totals_stride_k;
+    if (n_peers < 0 || n_peers > kMaxPeers) return fail(MB_EINVAL, "mb_step_fused_gather: at most %d peer buffers", kMaxPeers);
+    if (n_peers > 0 && (!totals_dev || !peer_totals)) return fail(MB_EINVAL, "mb_step_fused_gather: totals / peer list is NULL");
+    a.n_peers = n_peers;
+    a.peer_stride_k = peer_stride_k;
+    a.peer_stride_pair = peer_stride_pair;
+    if (n_peers > 0 && (peer_stride_k <= 0 || peer_stride_pair <= 0)) return fail(MB_EINVAL, "mb_step_fused_gather: peer strides must be positive");
+    for (int i = 0; i < n_peers; ++i) {
+        if (!peer_totals[i]) return fail(MB_EINVAL, "mb_step_fused_gather: peer buffer %d is NULL", i);
+        a.totals_peer[i] = peer_totals[i];
+    }
     a.forces_dec = forces_dec_dev; a.mask_dec = mask_dec_dev; a.forces_every = forces_every;
     a.forces_last = forces_last_dev;
     a.peripheral = cfg->peripheral_fatigue != 0;
@@ -863,4 +874,24 @@ extern "C" int mb_step_fused(const MbConfig* cfg, const void* params_dev, int64_
     if (g.U == 4) return MB_DISPATCH_FIB64(4);
     if (g.U == 2) return MB_DISPATCH_FIB64(2);
     return MB_DISPATCH_FIB64(1);
+}
+
+extern "C" int mb_step_fused(const MbConfig* cfg, const void* params_dev, int64_t M, int32_t n, int32_t K,
+                             const void* exc_dev, int64_t exc_stride_k, double* cpf_dev, double* dur_dev,
+                             void* totals_dev, int64_t totals_stride_k, void* forces_dec_dev, uint8_t* mask_dec_dev,
+                             int32_t forces_every, void* forces_last_dev, double step_size,
+                             int32_t units_per_thread, void* stream) {
+    return step_fused_impl(cfg, params_dev, M, n, K, exc_dev, exc_stride_k, cpf_dev, dur_dev, totals_dev,
+                           totals_stride_k, forces_dec_dev, mask_dec_dev, forces_every, forces_last_dev, step_size,
+                           units_per_thread, stream, nullptr, 0, 0, 0);
+}
+
+extern "C" int mb_step_fused_gather(const MbConfig* cfg, const void* params_dev, int64_t M, int32_t n, int32_t K,
+                                    const void* exc_dev, int64_t exc_stride_k, double* cpf_dev, double* dur_dev,
+                                    void* totals_dev, int64_t totals_stride_k, void* const* peer_totals_dev,
+                                    int32_t n_peers, int64_t peer_stride_k, int64_t peer_stride_pair,
+                                    void* forces_last_dev, double step_size, void* stream) {
+    return step_fused_impl(cfg, params_dev, M, n, K, exc_dev, exc_stride_k, cpf_dev, dur_dev, totals_dev,
+                           totals_stride_k, nullptr, nullptr, 0, forces_last_dev, step_size, 0, stream,
+                           peer_totals_dev, n_peers, peer_stride_k, peer_stride_pair);
 }

@@ -10,7 +10,10 @@ collective on the data path.  The only exchange is the optional gather of
 per-muscle totals (``gather=True`` / ``gather_totals``): one all-gather over
 ``torch.distributed`` (NCCL over NVLink on the GPUs, gloo in the CPU tests),
 issued per step or per fused window, optionally asynchronously so that it
-overlaps the next window.
+overlaps the next window -- or, for fused windows, ``gather="peer"``: the kernel
+itself stores every total into all GPUs' gather buffers (symmetric memory, plain
+stores over NVLink), so the gather overlaps the arithmetic step by step and no
+collective kernel runs at all.
 """
 from __future__ import annotations
 
@@ -125,8 +128,12 @@ class ShardedMuscleBatch:
         out = self.local.step(self._local_slice(excitation, False, global_input), step_size, **kw)
         return self.gather_totals(out) if gather else out
 
-    def step_many(self, excitations, step_size: float, gather: bool = False,
+    def step_many(self, excitations, step_size: float, gather=False,
                   global_input: Optional[bool] = None, **kw):
+        """``gather``: False (local totals), True (all-gather over torch.distributed) or "peer"
+        (the kernel stores into all GPUs' buffers; needs ``enable_peer_gather``)."""
+        if gather == "peer":
+            return self.step_many_peer_gather(excitations, step_size, global_input)
         per_step = kw.get("steps") is None                   # [M] + steps=K is the constant form
         out = self.local.step_many(self._local_slice(excitations, per_step, global_input), step_size, **kw)
         if gather:
@@ -134,6 +141,64 @@ class ShardedMuscleBatch:
             g = self.gather_totals(tot)
             return (g,) + tuple(out[1:]) if isinstance(out, tuple) else g
         return out
+
+    # ---- gather fused into the kernel: peer stores over NVLink -------------------------------
+    # Gather buffer (identical layout on every rank): one region per SOURCE rank r, pair-major:
+    #   region_r[pair][k][2],  pair = local muscle >> 1,  k < max_steps
+    # so the 32 lanes of a warp (32 steps of one muscle pair) store 256 contiguous bytes per tile.
+    def enable_peer_gather(self, max_steps: int):
+        """Collective.  Allocates two symmetric gather buffers per rank (double-buffered between
+        consecutive windows) and exchanges their mappings."""
+        import torch.distributed._symmetric_memory as symm_mem
+        if self.S != 1:
+            raise ValueError("the fused gather covers uniform batches")
+        group = self.group if self.group is not None else dist.group.WORLD
+        ks = int(max_steps)
+        pairs = [(m + 1) // 2 for m in self.sizes]
+        offs = [0]
+        for p in pairs:
+            offs.append(offs[-1] + p * ks * 2)
+        self._pg = {"steps": ks, "i": 0, "buf": [], "hdl": [], "pairs": pairs, "offs": offs}
+        for _ in range(2):
+            t = symm_mem.empty(offs[-1], dtype=self.local.dtype, device=self.local.device)
+            self._pg["buf"].append(t)
+            self._pg["hdl"].append(symm_mem.rendezvous(t, group))
+
+    def step_many_peer_gather(self, excitations: torch.Tensor, step_size: float,
+                              global_input: Optional[bool] = None, dense: bool = True):
+        """A fused window whose totals land in EVERY rank's gather buffer through the kernel's own
+        stores.  ``dense=True`` returns a contiguous [K, total muscles] tensor (one local re-layout
+        pass); ``dense=False`` returns the per-source-rank views [K, muscles_r] (strided, no copy),
+        valid until the window after next.  Consume the result on the current stream before
+        launching further windows."""
+        pg = getattr(self, "_pg", None)
+        if pg is None:
+            raise RuntimeError("call enable_peer_gather(max_steps) on every rank first")
+        e = self._local_slice(excitations, True, global_input)
+        K, ks = int(e.shape[0]), pg["steps"]
+        if K > ks:
+            raise ValueError(f"window of {K} steps exceeds enable_peer_gather({ks})")
+        b = pg["i"] & 1
+        pg["i"] += 1
+        buf, hdl = pg["buf"][b], pg["hdl"][b]
+        esz = buf.element_size()
+        off = pg["offs"][self.rank] * esz
+        peers = [hdl.get_buffer(r, (buf.numel(),), buf.dtype).data_ptr() + off
+                 for r in range(self.world) if r != self.rank]
+        local = torch.empty(K, self.n_muscles_local, dtype=buf.dtype, device=buf.device)
+        self.local.step_many_gather(e, step_size, local, peers, 2, 2 * ks)
+        hdl.barrier()                                           # every rank's stores have landed everywhere
+        views = []
+        for r in range(self.world):
+            if r == self.rank:
+                views.append(local)
+                continue
+            reg = buf[pg["offs"][r]: pg["offs"][r + 1]].view(pg["pairs"][r], ks, 2)
+            views.append(reg[:, :K].permute(1, 0, 2).reshape(K, -1)[:, : self.sizes[r]] if dense
+                         else reg[:, :K].permute(1, 0, 2))
+        if dense:
+            return torch.cat(views, dim=1)
+        return views
 
     # ---- the one exchange: all ranks' per-muscle totals ---------------------------------
     def gather_totals(self, local: torch.Tensor, async_op: bool = False):

@@ -258,6 +258,30 @@ class MuscleBatch:
             return (out, forces_dec, masks) if return_masks else (out, forces_dec)
         return out
 
+    # ---- K2 with the gather of totals fused into the kernel (multi-GPU) -----------------
+    def step_many_gather(self, excitations: torch.Tensor, step_size: float, out: torch.Tensor,
+                         peer_ptrs: Sequence[int], peer_stride_k: int, peer_stride_pair: int) -> None:
+        """``step_many`` whose totals go to ``out`` [K, M] (local) AND to raw device addresses in
+        every peer GPU's gather buffer (``peer_ptrs``, mapped through symmetric memory and already
+        offset to this rank's region; element (k, m) at (m >> 1) * peer_stride_pair +
+        k * peer_stride_k + (m & 1)) -- the kernel stores each total to all of them, so the
+        all-gather rides on the kernel's own stores over NVLink.  Uniform batches only; the
+        caller synchronises the ranks afterwards."""
+        e = excitations.to(device=self.device, dtype=self.dtype).contiguous()
+        M = self.n_muscles
+        assert self.S == 1 and e.dim() == 2 and e.shape[1] == M, "fused gather needs a uniform batch and exc [K, M]"
+        K = int(e.shape[0])
+        assert out.is_contiguous() and out.dtype == self.dtype and tuple(out.shape) == (K, M)
+        forces_last = torch.empty_like(self._forces) if self.fresh_outputs else self._forces
+        arr = (C.c_void_p * max(1, len(peer_ptrs)))(*[C.c_void_p(int(p)) for p in peer_ptrs])
+        with torch.cuda.device(self.device):
+            nat.check(nat.lib().mb_step_fused_gather(
+                C.byref(self.cfg), _ptr(self._params), M, self.L, K, _ptr(e), M, _ptr(self.cpf), _ptr(self.dur),
+                _ptr(out), M, arr, len(peer_ptrs), int(peer_stride_k), int(peer_stride_pair), _ptr(forces_last),
+                float(step_size), self._stream()))
+        self.launches += 1
+        self._forces = forces_last
+
     # ---- K2 with host buffers: H2D / compute / D2H pipelined over sub-windows ---------
     def step_many_host(self, exc_host: torch.Tensor, step_size: float, out_host: torch.Tensor,
                        chunk: int = 104, overlap_calls: bool = False) -> torch.Tensor:
