@@ -203,6 +203,22 @@ def measured_hbm_peak():
         return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md); MEASURED_PEAKS.json absent"
 
 
+def bind_to_gpu_numa_node(device_index):
+    """Pin this process to the CPUs closest to its GPU (NVML's ideal affinity) so that the pinned
+    staging buffers of the end-to-end leg are first-touched on the GPU's own NUMA node.  Several
+    ranks streaming through one socket's memory controllers otherwise throttle each other."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+        h = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return True
+    except Exception:
+        return False
+
+
 def run_gpu_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -220,6 +236,8 @@ def run_gpu_arm(args):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if world > 1:
+        bind_to_gpu_numa_node(local_rank)                     # pinned host buffers land next to this GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 

@@ -545,21 +545,13 @@ static int launch_k1(const MbConfig& c, const void* params, int64_t rows, int64_
     int tx = (int)((mean_n + 31) / 32) * 32;
     if (tx > 256) tx = 256;
     if (tx < 32) tx = 32;
-    const int R = env_int("MB_K1_R", 8);                      // rows advanced together by a block
+    constexpr int R = 8;                                      // rows advanced together by a block
     const int64_t items = ((rows + R - 1) / R) * S;
     int64_t blocks = items;
     const int64_t cap = (int64_t)sm_count() * (2048 / tx) * 4;   // a few waves of resident blocks
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    const int minb = env_int("MB_K1_MINB", 3);
-    if (R == 4) {
-        if (minb >= 4) k1_step<T, 4, 4><<<(unsigned)blocks, tx, 0, st>>>(a);
-        else k1_step<T, 4, 2><<<(unsigned)blocks, tx, 0, st>>>(a);
-    } else {
-        if (minb >= 4) k1_step<T, 8, 4><<<(unsigned)blocks, tx, 0, st>>>(a);
-        else if (minb == 3) k1_step<T, 8, 3><<<(unsigned)blocks, tx, 0, st>>>(a);
-        else k1_step<T, 8, 2><<<(unsigned)blocks, tx, 0, st>>>(a);
-    }
+    k1_step<T, R, 2><<<(unsigned)blocks, tx, 0, st>>>(a);
     MB_CUDA_OK(cudaGetLastError());
     return MB_OK;
 }
