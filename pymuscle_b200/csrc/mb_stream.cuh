@@ -97,10 +97,10 @@ __global__ void __launch_bounds__(288, 2) k1_stream(const K1sArgs<T> a) {
     const uint32_t bar0 = smem_u32(smem_raw);             // full[NS] | empty[NS]
     double* cpf_s = (double*)(smem_raw + 128);            // [NS][R][rowp]
     double* dur_s = cpf_s + (size_t)NS * R * rowp;        // [NS][R][rowp]   (CENTRAL only)
-    T* red = (T*)(CENTRAL ? dur_s + (size_t)NS * R * rowp : dur_s);   // [2R][8]: force sums | capacity sums
+    T* red0 = (T*)(CENTRAL ? dur_s + (size_t)NS * R * rowp : dur_s);  // [2 item parities][2R][8]: force sums | capacity sums
     // ragged rows: segment offsets and divisors are read once per work item by every thread ->
     // keep them in shared memory instead of paying a dependent global load per item
-    double* segdiv_s = (double*)(red + 2 * R * 8);        // [S]
+    double* segdiv_s = (double*)(red0 + 2 * 2 * R * 8);   // [S]
     int32_t* segoff_s = (int32_t*)(segdiv_s + (a.seg_in_smem ? a.S : 0));   // [S + 1]
     const int32_t* seg_off = a.seg_off;
     const double* seg_div = a.seg_div;
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(288, 2) k1_stream(const K1sArgs<T> a) {
 #pragma unroll
         for (int r = 0; r < R; ++r) x[r] = (item < items && r0 + r < a.rows) ? a.in[(r0 + r) * a.S + seg] : T(0);
     };
-    uint32_t it = 0;
+    uint32_t it = 0, item_no = 0;
     T xnext[R];
     fetch_inputs(blockIdx.x, xnext);
     for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
@@ -232,6 +232,9 @@ __global__ void __launch_bounds__(288, 2) k1_stream(const K1sArgs<T> a) {
             if (lane == 0) mbar_arrive(bar0 + 8u * (NS + s));    // this warp is done with the stage
         }
         if (a.totals || want_fatigue) {
+            // scratch alternates between consecutive items, so ONE barrier per item is enough: a warp
+            // reaches the next write of the same half only after the barrier of the item in between
+            T* red = red0 + (item_no++ & 1) * (2 * R * 8);
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const T w = warp_sum(partial[r]);
@@ -259,7 +262,6 @@ __global__ void __launch_bounds__(288, 2) k1_stream(const K1sArgs<T> a) {
                     a.fatigue[mu] = 1.0 - cs / (seg_div ? seg_div[seg] : a.fat_div);
                 }
             }
-            asm volatile("bar.sync 1, %0;" ::"r"(ncons) : "memory");
         }
     }
 }

@@ -615,7 +615,7 @@ static int launch_k1s(const MbConfig& c, const void* params, int64_t rows, int64
     a.W = W; a.NS = NS;
     const int threads = W + 32;
     a.seg_in_smem = (seg_off != nullptr && S <= 2048) ? 1 : 0;
-    const int smem = 128 + NS * stage_bytes + 2 * kStreamRows * 8 * (int)sizeof(T) + (a.seg_in_smem ? S * 8 + (S + 1) * 4 + 8 : 0);
+    const int smem = 128 + NS * stage_bytes + 4 * kStreamRows * 8 * (int)sizeof(T) + (a.seg_in_smem ? S * 8 + (S + 1) * 4 + 8 : 0);
     const int64_t items = ((rows + kStreamRows - 1) / kStreamRows) * S;
 #define MB_K1S_F(C_, R_, F_) (fatigue ? launch_k1s_variant<T, C_, R_, F_, true>(a, threads, smem, items, st) \
                                        : launch_k1s_variant<T, C_, R_, F_, false>(a, threads, smem, items, st))
