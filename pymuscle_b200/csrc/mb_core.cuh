@@ -36,22 +36,34 @@ struct UnitD {
     double thr, peak, phir, phir6, ctA, ctB, fat, ptf, rec, rdi;
 };
 
-__device__ __forceinline__ UnitF load_unit(const float4* __restrict__ P, int64_t L, int64_t i) {
-    const float4 a = __ldg(P + i), b = __ldg(P + L + i), c = __ldg(P + 2 * L + i);
+__device__ __forceinline__ UnitF make_unit(const float4 a, const float4 b, const float4 c) {
     UnitF u;
     u.crit = a.x; u.thr_g = a.y; u.peak = a.z; u.phir = a.w;
     u.phir6 = b.x; u.ctA = b.y; u.ctB = b.z; u.fat = b.w;
     u.ptf = c.x; u.ptf_lo2 = c.y; u.rdi = c.z; u.ptf_lo = c.w;
     return u;
 }
-
-__device__ __forceinline__ UnitD load_unit(const double2* __restrict__ P, int64_t L, int64_t i) {
-    const double2 a = __ldg(P + i), b = __ldg(P + L + i), c = __ldg(P + 2 * L + i),
-                  d = __ldg(P + 3 * L + i), e = __ldg(P + 4 * L + i);
+__device__ __forceinline__ UnitD make_unit(const double2 a, const double2 b, const double2 c, const double2 d,
+                                           const double2 e) {
     UnitD u;
     u.thr = a.x; u.peak = a.y; u.phir = b.x; u.phir6 = b.y; u.ctA = c.x; u.ctB = c.y;
     u.fat = d.x; u.ptf = d.y; u.rec = e.x; u.rdi = e.y;
     return u;
+}
+
+// from the global table [group][L] (read-only path)
+__device__ __forceinline__ UnitF load_unit(const float4* __restrict__ P, int64_t L, int64_t i) {
+    return make_unit(__ldg(P + i), __ldg(P + L + i), __ldg(P + 2 * L + i));
+}
+__device__ __forceinline__ UnitD load_unit(const double2* __restrict__ P, int64_t L, int64_t i) {
+    return make_unit(__ldg(P + i), __ldg(P + L + i), __ldg(P + 2 * L + i), __ldg(P + 3 * L + i), __ldg(P + 4 * L + i));
+}
+// from a staged tile [group][W] in shared memory
+__device__ __forceinline__ UnitF load_unit_staged(const float4* P, int W, int i) {
+    return make_unit(P[i], P[W + i], P[2 * W + i]);
+}
+__device__ __forceinline__ UnitD load_unit_staged(const double2* P, int W, int i) {
+    return make_unit(P[i], P[W + i], P[2 * W + i], P[3 * W + i], P[4 * W + i]);
 }
 
 // Scalars derived from MbConfig by the launcher (host, float64) -- passed by value.

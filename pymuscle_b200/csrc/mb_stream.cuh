@@ -11,9 +11,11 @@
 //                   lane r; SASS UBLKCP), completion counted on the stage's `full` mbarrier
 //                   (expect_tx).  NS stages deep: (NS-1) * R * W * 8 B per state array are
 //                   in flight per block regardless of what the consumer warps are doing.
-//   consumer warps  thread tx owns unit u0 + tx of the tile in all R rows: it loads the
-//                   unit's packed parameters once (L2), waits for the stage, reads its R
-//                   state values from shared memory, runs the step arithmetic
+//                   The tile's packed unit parameters ([groups][W] 128-bit vectors, L2-resident
+//                   table) ride along in the same stage, one bulk copy per group.
+//   consumer warps  thread tx owns unit u0 + tx of the tile in all R rows: it waits for the
+//                   stage, reads its parameters and its R state values from shared memory (no
+//                   exposed global-load latency in the consumers), runs the step arithmetic
 //                   (mb_core.cuh) and writes forces / new state straight to HBM with
 //                   coalesced stores.  Per-muscle partial sums stay in registers across the
 //                   segment's column tiles and are reduced once per work item (warp
@@ -31,8 +33,8 @@ namespace mb {
 constexpr int kStreamRows = 8;          // R: rows advanced together by a block
 
 template <typename T> struct StreamTraits;
-template <> struct StreamTraits<float>  { using U = UnitF; using P = float4;  using S = ScalF; };
-template <> struct StreamTraits<double> { using U = UnitD; using P = double2; using S = ScalD; };
+template <> struct StreamTraits<float>  { using U = UnitF; using P = float4;  using S = ScalF; static constexpr int G = kGroupsF32; };
+template <> struct StreamTraits<double> { using U = UnitD; using P = double2; using S = ScalD; static constexpr int G = kGroupsF64; };
 
 template <typename T>
 struct K1sArgs {
@@ -95,9 +97,12 @@ __global__ void __launch_bounds__(288, 2) k1_stream(const K1sArgs<T> a) {
     const int W = a.W, NS = a.NS;
     const int rowp = W + 2;                               // stage row pitch in elements (shift + round-up slack)
     const uint32_t bar0 = smem_u32(smem_raw);             // full[NS] | empty[NS]
+    using P = typename StreamTraits<T>::P;
+    constexpr int G = StreamTraits<T>::G;
     double* cpf_s = (double*)(smem_raw + 128);            // [NS][R][rowp]
     double* dur_s = cpf_s + (size_t)NS * R * rowp;        // [NS][R][rowp]   (CENTRAL only)
-    T* red0 = (T*)(CENTRAL ? dur_s + (size_t)NS * R * rowp : dur_s);  // [2 item parities][2R][8]: force sums | capacity sums
+    P* par_s = (P*)(CENTRAL ? dur_s + (size_t)NS * R * rowp : dur_s);     // [NS][G][W] staged unit parameters
+    T* red0 = (T*)(par_s + (size_t)NS * G * W);           // [2 item parities][2R][8]: force sums | capacity sums
     // ragged rows: segment offsets and divisors are read once per work item by every thread ->
     // keep them in shared memory instead of paying a dependent global load per item
     double* segdiv_s = (double*)(red0 + 2 * 2 * R * 8);   // [S]
@@ -144,13 +149,19 @@ __global__ void __launch_bounds__(288, 2) k1_stream(const K1sArgs<T> a) {
                 const int64_t e0 = off0 + u0;             // element offset inside a row
                 const int64_t a0 = e0 & ~(int64_t)1, a1 = (e0 + count + 1) & ~(int64_t)1;
                 const uint32_t bytes = (uint32_t)(a1 - a0) * 8u;
-                if (lane == 0) mbar_expect_tx(bar0 + 8u * s, bytes * nrows * (CENTRAL ? 2u : 1u));
+                const uint32_t pbytes = (uint32_t)count * 16u;           // one parameter group of the tile
+                if (lane == 0) mbar_expect_tx(bar0 + 8u * s, bytes * nrows * (CENTRAL ? 2u : 1u) + pbytes * G);
                 __syncwarp();
                 if (lane < nrows) {
                     const int64_t g = (r0 + lane) * a.L + a0;
                     const uint32_t so = (uint32_t)((s * R + lane) * rowp) * 8u;
                     bulk_g2s(smem_u32(cpf_s) + so, a.cpf + g, bytes, bar0 + 8u * s);
                     if (CENTRAL) bulk_g2s(smem_u32(dur_s) + so, a.dur + g, bytes, bar0 + 8u * s);
+                }
+                if (lane >= R && lane < R + G) {
+                    const int grp = lane - R;                            // lanes R .. R+G-1: the parameter groups
+                    bulk_g2s(smem_u32(par_s + (size_t)(s * G + grp) * W), a.params + (int64_t)grp * a.L + e0, pbytes,
+                             bar0 + 8u * s);
                 }
             }
         }
@@ -189,12 +200,12 @@ __global__ void __launch_bounds__(288, 2) k1_stream(const K1sArgs<T> a) {
             const uint32_t s = it % NS, ph = (it / NS) & 1;
             const int u = u0 + tid;
             const bool active = u < n;
-            const auto p = load_unit(a.params, a.L, off0 + (active ? u : 0));
-            const double fatdt = (double)p.fat * a.dt, rdidt = (double)p.rdi * a.dt;
-            const double ptf = unit_peak(p);
             const int shift = (off0 + u0) & 1;
             mbar_wait(bar0 + 8u * s, ph);
             if (active) {
+                const auto p = load_unit_staged(par_s + (size_t)(s * G) * W, W, tid);
+                const double fatdt = (double)p.fat * a.dt, rdidt = (double)p.rdi * a.dt;
+                const double ptf = unit_peak(p);
                 const double* cs = cpf_s + (s * R) * rowp + shift + tid;
                 const double* ds = dur_s + (s * R) * rowp + shift + tid;
                 double c[R], d[R];

@@ -607,9 +607,9 @@ static int launch_k1s(const MbConfig& c, const void* params, int64_t rows, int64
     const int wmax = env_int("MB_K1_W", 256);
     if (W > wmax) W = wmax;
     if (W < 32) W = 32;
-    const int stage_bytes = kStreamRows * (W + 2) * 8 * (central ? 2 : 1);
+    const int stage_bytes = kStreamRows * (W + 2) * 8 * (central ? 2 : 1) + StreamTraits<T>::G * W * 16;   // state rows + unit parameters
     int NS = env_int("MB_K1_STAGES", 0);
-    if (NS <= 0) NS = 3;                                      // measured: 3 stages x 2+ blocks/SM saturate HBM; deeper rings only cost occupancy
+    if (NS <= 0) NS = 2;                                      // measured: double buffering x 2+ blocks/SM saturates HBM; deeper rings only cost occupancy
     if (NS > 8) NS = 8;
     if (NS < 2) NS = 2;
     a.W = W; a.NS = NS;
