@@ -155,6 +155,54 @@ class MuscleBatch:
             self._forces = forces
         return self._shape_out(out.view(self.rows, self.S))
 
+    # ---- K1 for the scalar drop-in API: zero-copy host I/O ---------------------------------
+    def step_hostio(self, excitation, step_size: float) -> np.ndarray:
+        """One step whose input, totals and per-unit forces live in pinned HOST memory that the
+        kernel reads and writes directly (zero-copy over PCIe): a step is ONE kernel launch and
+        ONE stream synchronisation -- no fill kernel for the scalar excitation, no device-to-host
+        copies.  For the batch-of-1 drop-in classes (Muscle.step -> np.float64), where launch
+        latency is everything.  Returns the totals as a host array [rows, S] (a view that the
+        next call overwrites); ``host_forces()`` gives the per-unit forces of this step."""
+        h = getattr(self, "_hostio", None)
+        if h is None:
+            npdt = np.float32 if self.dtype == torch.float32 else np.float64
+            mk = lambda *shape: torch.zeros(*shape, dtype=self.dtype).pin_memory()
+            h = dict(x=mk(self.rows, self.S), xu=mk(self.rows, self.L), out=mk(self.rows, self.S),
+                     forces=mk(self.rows, self.L))
+            h["x_np"], h["xu_np"] = h["x"].numpy(), h["xu"].numpy()
+            h["out_np"], h["forces_np"] = h["out"].numpy(), h["forces"].numpy()
+            h["stream"] = torch.cuda.current_stream(self.device)
+            h["npdt"] = npdt
+            self._hostio = h
+        if isinstance(excitation, (int, float)):
+            h["x_np"].fill(excitation)
+            src, per_unit = h["x"], 0
+        else:
+            a = np.asarray(excitation, dtype=h["npdt"])
+            if a.size == self.n_muscles:
+                h["x_np"][...] = a.reshape(self.rows, self.S)
+                src, per_unit = h["x"], 0
+            elif a.size == self.n_units:
+                h["xu_np"][...] = a.reshape(self.rows, self.L)
+                src, per_unit = h["xu"], 1
+            else:
+                raise AssertionError(f"excitation has {a.size} elements; expected {self.n_muscles} or {self.n_units}")
+        st = torch.cuda.current_stream(self.device)
+        with torch.cuda.device(self.device):
+            nat.check(nat.lib().mb_step(
+                C.byref(self.cfg), _ptr(self._params), self.rows, self.L, self.S,
+                _ptr(self._seg_off), _ptr(self._seg_div), nat.MB_STAGE_MUSCLE, _ptr(src), per_unit,
+                _ptr(self.cpf), _ptr(self.dur), _ptr(h["forces"]), _ptr(h["out"]), None, None,
+                float(step_size), C.c_void_p(st.cuda_stream)))
+        self.launches += 1
+        st.synchronize()
+        self._forces_on_host = True
+        return h["out_np"]
+
+    def host_forces(self) -> np.ndarray:
+        """Per-unit forces of the last ``step_hostio`` call, as a FRESH host array (fibers:258)."""
+        return np.array(self._hostio["forces_np"], dtype=np.float64)
+
     # ---- K1 with the fused environment epilogue -------------------------------------------
     def step_env(self, excitation, step_size: float, gain: Optional[torch.Tensor] = None,
                  want_fatigue: bool = True):

@@ -96,7 +96,9 @@ class PotvinFuglevand2017MuscleFibers(Model):
     def current_forces(self) -> np.ndarray:
         """Per-unit forces of the last step: a new array per step (fibers:258)."""
         if self._forces_host is None:
-            self._forces_host = self._engine.current_forces[0].cpu().numpy()
+            src = getattr(self, "_forces_src", None)            # set by Muscle.step (fused launch, host I/O)
+            self._forces_host = src.host_forces()[0] if src is not None else \
+                self._engine.current_forces[0].cpu().numpy()
         return self._forces_host
 
     @property
@@ -113,6 +115,7 @@ class PotvinFuglevand2017MuscleFibers(Model):
         assert (len(motor_pool_output) == self.motor_unit_count)
         x = np.ascontiguousarray(motor_pool_output, dtype=np.float64)
         total = self._engine.step(x, step_size, stage=nat.MB_STAGE_FIBERS)
+        self._forces_src = None
         self._forces_host = None
         return np.float64(total.item())
 

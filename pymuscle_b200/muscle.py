@@ -66,11 +66,13 @@ class Muscle(object):
         else:
             x = np.array(motor_pool_input, dtype=np.float64)                   # muscle.py:89
             assert (len(x) == self.motor_unit_count)                           # pool:294
-        total = self._engine.step(x, step_size)
-        # hand the fresh per-unit forces to the fibers model (fibers:258)
-        self._fibers._engine._forces = self._engine.current_forces
+        # one launch + one stream sync: excitation, total and per-unit forces go through pinned
+        # host memory that the kernel reads / writes directly (MuscleBatch.step_hostio)
+        total = self._engine.step_hostio(x, step_size)[0, 0]
+        # the fibers model hands out the per-unit forces of this step as a fresh array (fibers:258)
+        self._fibers._forces_src = self._engine
         self._fibers._forces_host = None
-        return np.float64(total.item())
+        return np.float64(total)
 
 
 class PotvinFuglevandMuscle(Muscle):
