@@ -87,7 +87,9 @@ typedef struct MbConfig {
 
 /* Facts about a packed table that let the fused kernel drop provably dead clamps. */
 enum MbTableProps {
-    MB_PROP_ADAPT_NONNEG = 1   /* the adaptation of a recruited unit is never negative (pool:221 is a no-op) */
+    MB_PROP_ADAPT_NONNEG = 1,  /* the adaptation of a recruited unit is never negative (pool:221 is a no-op), gain and
+                                  minimal firing rate are positive (rate > 0 <=> recruited) */
+    MB_PROP_EXP_BOUNDED = 2    /* 2 * (ct_cur * rate / 1000)^3 stays below 600 for every unit: exp(-2x^3) cannot underflow */
 };
 
 int mb_abi_version(void);

@@ -19,7 +19,7 @@ MB_OK, MB_EINVAL, MB_EUNSUPPORTED, MB_ECUDA = 0, -1, -2, -3
 MB_F32, MB_F64 = 0, 1
 MB_FIBERS_POTVIN, MB_FIBERS_PYMUSCLE = 0, 1
 MB_STAGE_MUSCLE, MB_STAGE_POOL, MB_STAGE_FIBERS = 0, 1, 2
-MB_PROP_ADAPT_NONNEG = 1
+MB_PROP_ADAPT_NONNEG, MB_PROP_EXP_BOUNDED = 1, 2
 
 #: every symbol include/muscle_b200.h declares (tests check the .so exports them all)
 SYMBOLS = (

@@ -159,8 +159,9 @@ __constant__ double kExp2Tab[32] = {
 // as many): x = n*ln2/32 + r, |r| <= ln2/64, exp(x) = 2^(n>>5) * 2^((n&31)/32) * P5(r).
 // Relative error < 1e-14 (truncation r^6/720 = 2e-15, two-step reduction); the FP64 mode's
 // bar is 1e-9.  `tab` is a shared-memory copy of kExp2Tab (divergent index).
+template <bool CLAMP>
 __device__ __forceinline__ double exp_neg_fast(double x, const double* tab) {
-    x = fmax(x, -700.0);
+    if (CLAMP) x = fmax(x, -700.0);                                     // (the launcher proves it redundant for most tables)
     const double kMagic = 6755399441055744.0;                          // 1.5 * 2^52: round to integer
     const double t = fma(x, 0x1.71547652b82fep+5, kMagic);              // x * 32/ln2
     const int n = __double2loint(t);
@@ -177,6 +178,7 @@ __device__ __forceinline__ double exp_neg_fast(double x, const double* tab) {
 }
 
 // fibers_force with the fast exponential (fused kernel)
+template <bool CLAMP>
 __device__ __forceinline__ double fibers_force_fast(const UnitD& p, const ScalD& s, double fr, double cpf, double& nf,
                                                     const double* tab) {
     const double ctk = fma(cpf, -p.ctB, p.ctA);
@@ -184,7 +186,7 @@ __device__ __forceinline__ double fibers_force_fast(const UnitD& p, const ScalD&
     if (x <= kLinThrD) {
         nf = x * s.c25;
     } else {
-        nf = 1.0 - exp_neg_fast(-2.0 * (x * x * x), tab);
+        nf = 1.0 - exp_neg_fast<CLAMP>(-2.0 * (x * x * x), tab);
     }
     return nf * cpf;
 }

@@ -411,10 +411,20 @@ struct CoreF64 {
             for (int j = 0; j < U; ++j) E[j] = exp(dur[j] * sc.mitau);     // pool:217-218
         }
     }
+    // CENTRAL: 0 = no adaptation, 2 = general, 1 = fast path (as in FP32 mode): the launcher has
+    // checked that the adaptation of a recruited unit cannot be negative, that gain and minimal rate
+    // are positive (so "rate > 0" is the recruitment mask), that the duration clamp cannot change
+    // exp(-dur/tau) in float64, and that the sigmoid's exponent stays above -700
     __device__ __forceinline__ double step(int j, double e, bool& on) {
         const double r = pool_rate(p, sc, e, on);
         double fr = r;
-        if (CENTRAL) {
+        if (CENTRAL == 1) {
+            const double q = fma(r, p.phir, -p.phir6);                     // pool:231-232
+            fr = on ? fma(-q, 1.0 - E[j], r) : 0.0;                        // pool:217-221, :121 (dur BEFORE the update)
+            const double dn = fmin(dur[j] + dt, max_dur);                  // pool:196-203
+            dur[j] = on ? dn : dur[j];
+            E[j] = on ? E[j] * decay : E[j];
+        } else if (CENTRAL == 2) {
             const double q = fma(r, p.phir, -p.phir6);                     // pool:231-232
             const double ad = q * (1.0 - E[j]);                            // pool:217-219 (dur BEFORE the update)
             fr = r - ((ad < 0.0) ? 0.0 : ad);                              // pool:221, :121
@@ -426,7 +436,7 @@ struct CoreF64 {
             }
         }
         double nf;
-        const double F = fibers_force_fast(p, sc, fr, cpf[j], nf, tab);
+        const double F = fibers_force_fast<CENTRAL != 1>(p, sc, fr, cpf[j], nf, tab);
         cpf[j] = fatigue_update<FIB == MB_FIBERS_PYMUSCLE>(cpf[j], nf, fatdt, rdidt, p.ptf);
         return F;
     }

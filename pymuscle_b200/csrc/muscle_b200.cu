@@ -133,13 +133,15 @@ extern "C" int mb_params_pack(const MbConfig* cfg, int64_t L, const double* thr,
     const double ccr = cfg->contraction_time_change_ratio;
     // A recruited unit fires at >= gain*minR, so q = phi*ratio*(r - (minR - d)) >= 0 for every
     // recruited unit iff phi*ratio >= 0 and gain*minR clears minR - d (with float slack).
-    bool adapt_nonneg = (g * minr) * (1.0 - 1e-5) > (minr - dd);
+    bool adapt_nonneg = (g * minr) * (1.0 - 1e-5) > (minr - dd) && g > 0.0 && minr > 0.0;
+    double xmax = 0.0;                        // largest normalised firing rate ct_cur * rate / 1000 any unit can reach
     for (int64_t i = 0; i < L; ++i) {
         const double ratio = (thr[i] - 1.0) / (rr - 1.0);                 // pool:231
         const double phir = phi * ratio;
         const double phir6 = phir * (minr - dd);
         adapt_nonneg = adapt_nonneg && (phir >= 0.0);
         const double ctA = ct[i] * (1.0 + ccr) / 1000.0;
+        if (ctA * peak[i] > xmax) xmax = ctA * peak[i];
         const double ctB = ct[i] * ccr / (1000.0 * ptf[i]);
         const double r = rec ? rec[i] : 0.0;
         const double rdi = r / ptf[i];
@@ -161,7 +163,8 @@ extern "C" int mb_params_pack(const MbConfig* cfg, int64_t L, const double* thr,
             P[4 * L + i] = make_double2(r, rdi);
         }
     }
-    if (table_props) *table_props = adapt_nonneg ? MB_PROP_ADAPT_NONNEG : 0;
+    if (table_props)
+        *table_props = (adapt_nonneg ? MB_PROP_ADAPT_NONNEG : 0) | ((2.0 * xmax * xmax * xmax < 600.0) ? MB_PROP_EXP_BOUNDED : 0);
     return MB_OK;
 }
 
@@ -776,8 +779,7 @@ static int launch_fused(KernelT kernel, const K2Args& a, const FusedGeom& g, cud
 #define MB_DISPATCH_FIB(KERN, UU)                                                              \
     (fib == MB_FIBERS_POTVIN ? MB_DISPATCH_CENTRAL(KERN, MB_FIBERS_POTVIN, UU)                  \
                              : MB_DISPATCH_CENTRAL(KERN, MB_FIBERS_PYMUSCLE, UU))
-#define MB_DISPATCH_CENTRAL64(FIB, UU)                                                         \
-    (cen == 0 ? MB_DISPATCH_FORCES(k2_fused_f64, FIB, 0, UU) : MB_DISPATCH_FORCES(k2_fused_f64, FIB, 1, UU))
+#define MB_DISPATCH_CENTRAL64(FIB, UU) MB_DISPATCH_CENTRAL(k2_fused_f64, FIB, UU)
 #define MB_DISPATCH_FIB64(UU)                                                                  \
     (fib == MB_FIBERS_POTVIN ? MB_DISPATCH_CENTRAL64(MB_FIBERS_POTVIN, UU) : MB_DISPATCH_CENTRAL64(MB_FIBERS_PYMUSCLE, UU))
 
@@ -862,7 +864,9 @@ static int step_fused_impl(const MbConfig* cfg, const void* params_dev, int64_t 
         if (g.U == 2) return MB_DISPATCH_FIB(k2_fused_f32, 2);
         return MB_DISPATCH_FIB(k2_fused_f32, 1);
     }
-    if (cen == 2) cen = 1;      // FP64 always applies both clamps (duration_update / pool_adapt)
+    // FP64: the fast path additionally needs the sigmoid's exponent bounded (no clamp in exp_neg_fast);
+    // without central fatigue the clamp is kept (CENTRAL == 0 instantiates it)
+    if (cen == 1 && !(cfg->table_props & MB_PROP_EXP_BOUNDED)) cen = 2;
     if (g.U == 4) return MB_DISPATCH_FIB64(4);
     if (g.U == 2) return MB_DISPATCH_FIB64(2);
     return MB_DISPATCH_FIB64(1);
