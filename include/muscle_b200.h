@@ -82,7 +82,9 @@ typedef struct MbConfig {
     double input_scale;    /* 1, or Pool.max_excitation for StandardMuscle (muscle.py:275) */
     double output_divisor; /* 1, or StandardMuscle.max_arb_output          (muscle.py:278) */
     int32_t table_props;   /* MbTableProps bits returned by mb_params_pack for the table in use */
-    int32_t reserved;
+    int32_t param_rows;    /* 0 or 1: one parameter table shared by all rows (the reference's case: identical muscles);
+                              N > 1: per-instance hyper-parameters -- params_dev holds N consecutive packed tables and
+                              row r of a uniform batch (S == 1, rows == N) uses table r (domain randomisation) */
 } MbConfig;
 
 /* Facts about a packed table that let the fused kernel drop provably dead clamps. */

@@ -46,7 +46,7 @@ class MbConfig(C.Structure):
         ("input_scale", C.c_double),
         ("output_divisor", C.c_double),
         ("table_props", C.c_int32),
-        ("reserved", C.c_int32),
+        ("param_rows", C.c_int32),
     ]
 
 

@@ -46,6 +46,7 @@ constexpr int kFtPitch = 33;     // row pitch of a warp's force tile, in vectors
 
 struct K2Args {
     const void* params;
+    int64_t param_stride;        // 0: one shared table; else 128-bit vectors between the tables of consecutive muscles
     int64_t M;
     int32_t n, ns, q, K, T, G, Gp, npg, ptp;   // ns: threads per muscle group; npg = ns/8 parts per group; ptp: PT row pitch
     const void* exc;
@@ -326,8 +327,8 @@ struct CoreF32 {
     float inv_out;
     PairState st[NP];
 
-    __device__ __forceinline__ void load(const K2Args& a, int unit) {
-        u = load_unit((const float4*)a.params, a.n, unit);
+    __device__ __forceinline__ void load(const K2Args& a, int unit, int64_t muscle) {
+        u = load_unit((const float4*)a.params + muscle * a.param_stride, a.n, unit);
         p = pair_params(u, a);
         sc = pair_scal(a);
         inv_out = a.sf.inv_out;
@@ -387,8 +388,8 @@ struct CoreF64 {
     double cpf[U], dur[U], E[U];
     const double* tab;           // shared-memory copy of kExp2Tab
 
-    __device__ __forceinline__ void load(const K2Args& a, int u) {
-        p = load_unit((const double2*)a.params, a.n, u);
+    __device__ __forceinline__ void load(const K2Args& a, int u, int64_t muscle) {
+        p = load_unit((const double2*)a.params + muscle * a.param_stride, a.n, u);
         sc = a.sd;
         fatdt = a.peripheral ? p.fat * a.dt : 0.0;
         rdidt = a.peripheral ? p.rdi * a.dt : 0.0;
@@ -546,7 +547,7 @@ __device__ __forceinline__ void k2_body(const K2Args& a) {
     const int u = has_unit ? u_raw : 0;
     Core core;
     core.set_table(exp2_tab);
-    core.load(a, u);
+    core.load(a, u, min(m0 + (int64_t)tq * U, a.M - 1));     // (per-instance tables: U == 1, the muscle's own table)
 #pragma unroll
     for (int j = 0; j < U; ++j) {
         const int g = tq * U + j;

@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MB_W_MINB) k2w_f32(const 
     for (int i = 0; i < UPL; ++i) {
         const int u = lane + 32 * i;
         const bool valid = u < n;
-        core[i].load(a, valid ? u : 0);
+        core[i].load(a, valid ? u : 0, 0);
         if (!valid) core[i].disable();                                  // idle slot: never recruited, force 0
         if (valid) {
             core[i].init(0, a, a.cpf[m0 * n + u], CENTRAL ? a.dur[m0 * n + u] : 0.0);
@@ -166,6 +166,145 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MB_W_MINB) k2w_f32(const 
             core[i].store(0, a, m0 * n + u);
             if (two) core[i].store(1, a, (m0 + 1) * n + u);
         }
+    }
+}
+
+// ======================================================================================
+// K2u: one warp per MUSCLE, pairs of UNITS -- the fused kernel for per-instance parameter tables.
+//
+// Lane l holds units l, l+32 (one pair) and, for n > 64, l+64, l+96 (a second pair) of a single
+// muscle; the two units of a pair are the two halves of the packed operands, so the per-unit
+// parameters are register pairs too and every muscle can have its own table (domain
+// randomisation, MbConfig::param_rows) at no extra cost.  ~80 registers, three blocks per SM.
+// Everything else is K2w: private force tile, lane s sums row s, no cross-warp traffic.
+// (With one shared table it runs at 1.22e12 unit-steps/s against K2w's 1.33e12 on the headline
+// shape -- per-step overhead is spread over 4 instead of 8 unit-instances -- so K2w keeps that case.)
+// ======================================================================================
+constexpr int kUPitch = 34;      // row pitch of the float force tile (even: 64-bit row reads, conflict free)
+
+__device__ __forceinline__ float2 P2(float a, float b) { return make_float2(a, b); }
+
+template <int FIB, int CENTRAL, int NPU, bool FORCES>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) k2u_f32(const K2Args a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* ftw = (float*)smem_raw + warp * (kWTile * kUPitch + 2 * kWTile);     // [32][34]
+    float* excw = ftw + kWTile * kUPitch;                                        // [2][32]
+
+    const int n = a.n;
+    const int64_t m = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
+    if (m >= a.M) return;                                 // warps are independent: no barrier below
+    const int ntiles = (a.K + kWTile - 1) / kWTile;
+    const float* exc = (const float*)a.exc;
+    const PairScal sc = pair_scal(a);
+    const float inv_out = a.sf.inv_out;
+    const float4* table = (const float4*)a.params + m * a.param_stride;         // this muscle's own table
+
+    PairParams<float2> pp[NPU];
+    PairState st[NPU];
+#pragma unroll
+    for (int i = 0; i < NPU; ++i) {
+        const int u0 = lane + 64 * i, u1 = u0 + 32;
+        const UnitF a0 = load_unit(table, n, u0 < n ? u0 : 0);
+        const UnitF a1 = load_unit(table, n, u1 < n ? u1 : 0);
+        const PairParams<float> q0 = pair_params(a0, a), q1 = pair_params(a1, a);
+        const float inf = __int_as_float(0x7f800000);
+        pp[i].crit = P2(u0 < n ? q0.crit : inf, u1 < n ? q1.crit : inf);         // idle slot: never recruited, force 0
+        pp[i].thr_g = P2(q0.thr_g, q1.thr_g);   pp[i].peak = P2(q0.peak, q1.peak);
+        pp[i].phir = P2(q0.phir, q1.phir);      pp[i].phir6 = P2(q0.phir6, q1.phir6);
+        pp[i].ctA = P2(q0.ctA, q1.ctA);         pp[i].ctB = P2(q0.ctB, q1.ctB);
+        pp[i].fatdt = P2(q0.fatdt, q1.fatdt);   pp[i].rdidt = P2(q0.rdidt, q1.rdidt);
+        pp[i].ptf = P2(q0.ptf, q1.ptf);         pp[i].ptf_lo = P2(q0.ptf_lo, q1.ptf_lo);
+        pair_init(st[i], pp[i], 0, u0 < n ? a.cpf[m * n + u0] : unit_peak(a0),
+                  (CENTRAL && u0 < n) ? a.dur[m * n + u0] : 0.0, a.adk_d);
+        pair_init(st[i], pp[i], 1, u1 < n ? a.cpf[m * n + u1] : unit_peak(a1),
+                  (CENTRAL && u1 < n) ? a.dur[m * n + u1] : 0.0, a.adk_d);
+    }
+
+    // excitation of (tile, step = lane); 0 beyond the window.  exc_stride_k == 0: constant
+    auto fetch = [&](int tile) -> float {
+        const int k = tile * kWTile + lane;
+        return (k < a.K) ? __ldg(exc + (int64_t)k * a.exc_stride_k + m) : 0.0f;
+    };
+    float e_next = fetch(0);
+
+    for (int tile = 0; tile < ntiles; ++tile) {
+        const int k0 = tile * kWTile;
+        const int steps = min(kWTile, a.K - k0);
+        float* es = excw + (tile & 1) * kWTile;
+        es[lane] = e_next;
+        __syncwarp();
+        if (tile + 1 < ntiles) e_next = fetch(tile + 1);
+#pragma unroll
+        for (int i = 0; i < NPU; ++i) pair_begin_tile<CENTRAL>(st[i], sc);
+
+        auto do_step = [&](int s, auto last_tag) {
+            constexpr bool LAST = decltype(last_tag)::value;
+            const float e = es[s];
+            float2 fsum;
+            bool write_now = false;
+            if (FORCES) write_now = ((k0 + s + 1) % a.forces_every) == 0;
+#pragma unroll
+            for (int i = 0; i < NPU; ++i) {
+                bool oa, ob;
+                const float2 F = pair_step<FIB, CENTRAL>(st[i], pp[i], sc, make_float2(e, e), oa, ob);
+                fsum = (i == 0) ? F : __fadd2_rn(fsum, F);
+                if (FORCES || LAST) {
+                    const int u0 = lane + 64 * i, u1 = u0 + 32;
+                    if (FORCES && write_now) {
+                        const int64_t base = (int64_t)((k0 + s) / a.forces_every) * a.M * n + m * n;
+                        float* fd = (float*)a.forces_dec;
+                        if (u0 < n) fd[base + u0] = F.x;
+                        if (u1 < n) fd[base + u1] = F.y;
+                        if (a.mask_dec) {
+                            if (u0 < n) a.mask_dec[base + u0] = oa ? 1 : 0;
+                            if (u1 < n) a.mask_dec[base + u1] = ob ? 1 : 0;
+                        }
+                    }
+                    if (LAST) {
+                        float* fl = (float*)a.forces_last + m * n;
+                        if (u0 < n) fl[u0] = F.x;
+                        if (u1 < n) fl[u1] = F.y;
+                    }
+                }
+            }
+            ftw[s * kUPitch + lane] = fsum.x + fsum.y;
+        };
+        const bool has_last = a.forces_last != nullptr && tile == ntiles - 1;
+        const int fast_steps = has_last ? steps - 1 : steps;
+        for (int s = 0; s < fast_steps; ++s) do_step(s, std::false_type{});
+        if (has_last) do_step(steps - 1, std::true_type{});
+#pragma unroll
+        for (int i = 0; i < NPU; ++i) pair_renormalise<FIB>(st[i], pp[i]);
+        __syncwarp();
+        // ---- lane s sums the 32 lanes' forces of step k0 + s -----------------------------------
+        if (lane < steps) {
+            const float2* rp = (const float2*)(ftw + lane * kUPitch);
+            float2 acc0 = rp[0], acc1 = rp[1];
+#pragma unroll
+            for (int c = 2; c < 16; c += 2) {
+                acc0 = __fadd2_rn(acc0, rp[c]);
+                acc1 = __fadd2_rn(acc1, rp[c + 1]);
+            }
+            const float2 acc = __fadd2_rn(acc0, acc1);
+            if (a.totals) {
+                const float v = (acc.x + acc.y) * inv_out;
+                const int64_t o = (int64_t)(k0 + lane) * a.totals_stride_k + m;
+                ((float*)a.totals)[o] = v;
+                if (a.n_peers > 0) {
+                    const int64_t op = (m >> 1) * a.peer_stride_pair + (int64_t)(k0 + lane) * a.peer_stride_k + (m & 1);
+                    for (int pr = 0; pr < a.n_peers; ++pr) ((float*)a.totals_peer[pr])[op] = v;
+                }
+            }
+        }
+        __syncwarp();
+    }
+
+#pragma unroll
+    for (int i = 0; i < NPU; ++i) {
+        const int u0 = lane + 64 * i, u1 = u0 + 32;
+        if (u0 < n) pair_store<CENTRAL != 0>(st[i], 0, a, m * n + u0);
+        if (u1 < n) pair_store<CENTRAL != 0>(st[i], 1, a, m * n + u1);
     }
 }
 

@@ -180,6 +180,7 @@ template <> struct Vec<double> { using P = double2; using U = UnitD; using S = S
 template <typename T>
 struct K1Args {
     const typename Vec<T>::P* params;
+    int64_t param_stride;          // 0: one shared table; else vectors between the tables of consecutive rows
     int64_t rows, L;
     int32_t S;
     const int32_t* seg_off;
@@ -294,7 +295,7 @@ __global__ void __launch_bounds__(256, MINB) k1_step(const K1Args<T> a) {
             xm[r] = (!a.in_per_unit && r < nrows) ? a.in[(r0 + r) * a.S + seg] : T(0);
         }
         for (int u = tx; u < n; u += TX) {
-            const auto p = load_unit(a.params, a.L, off0 + u);
+            auto p = load_unit(a.params + r0 * a.param_stride, a.L, off0 + u);
             const int64_t i0 = r0 * a.L + off0 + u;
             double c[R], d[R];
             T x[R];
@@ -310,6 +311,7 @@ __global__ void __launch_bounds__(256, MINB) k1_step(const K1Args<T> a) {
             for (int r = 0; r < R; ++r) {
                 if (r >= nrows) continue;
                 const int64_t i = i0 + (int64_t)r * a.L;
+                if (a.param_stride && r > 0) p = load_unit(a.params + (r0 + r) * a.param_stride, a.L, off0 + u);
                 K1Out o;
                 T rate = 0;
                 const T F = k1_compute(a, p, x[r], c[r], d[r], o, rate);
@@ -532,6 +534,7 @@ static int launch_k1(const MbConfig& c, const void* params, int64_t rows, int64_
                      cudaStream_t st, const typename Vec<T>::S& sc) {
     K1Args<T> a;
     a.params = (const typename Vec<T>::P*)params;
+    a.param_stride = c.param_rows > 1 ? (int64_t)(sizeof(T) == 4 ? kGroupsF32 : kGroupsF64) * L : 0;
     a.rows = rows; a.L = L; a.S = S; a.seg_off = seg_off; a.seg_div = seg_div;
     a.stage = stage; a.in_per_unit = in_per_unit;
     a.recovery = c.fibers_kind == MB_FIBERS_PYMUSCLE;
@@ -582,7 +585,7 @@ static int launch_k1s_variant(const K1sArgs<T>& a, int threads, int smem, int64_
 template <typename T>
 static bool k1s_eligible(const MbConfig& c, int64_t L, int32_t stage, int32_t in_per_unit, const double* cpf,
                          const double* dur, const uint8_t* mask, const void* rates) {
-    if (env_int("MB_K1_GENERIC", 0)) return false;
+    if (env_int("MB_K1_GENERIC", 0) || c.param_rows > 1) return false;       // per-instance tables: generic kernel
     if (stage != MB_STAGE_MUSCLE || in_per_unit || mask || rates || !c.peripheral_fatigue) return false;
     if (L % 2 != 0 || ((uintptr_t)cpf % 16) != 0) return false;
     if (c.central_fatigue && ((uintptr_t)dur % 16) != 0) return false;
@@ -641,6 +644,8 @@ extern "C" int mb_step(const MbConfig* cfg, const void* params_dev, int64_t rows
     if (stage != MB_STAGE_POOL && !cpf_dev) return fail(MB_EINVAL, "mb_step: cpf is NULL");
     if (stage != MB_STAGE_FIBERS && cfg->central_fatigue && !dur_dev) return fail(MB_EINVAL, "mb_step: dur is NULL");
     if (stage == MB_STAGE_FIBERS && !in_per_unit) return fail(MB_EINVAL, "mb_step: firing rates must be per unit");
+    if (cfg->param_rows > 1 && (S != 1 || cfg->param_rows != rows))
+        return fail(MB_EINVAL, "mb_step: per-instance tables need a uniform batch with param_rows == rows");
     cudaStream_t st = (cudaStream_t)stream;
     if (cfg->precision == MB_F32) {
         if (k1s_eligible<float>(*cfg, L, stage, in_per_unit, cpf_dev, dur_dev, mask_dev, rates_dev))
@@ -699,7 +704,8 @@ extern "C" int mb_peripheral_fatigue(const MbConfig* cfg, int64_t rows, int64_t 
 struct FusedGeom {
     int U, q, G, Gp, T, ns, npg, ptp, threads, smem;
     int64_t blocks;
-    int warp_kernel;      // 1: k2w_f32 (one warp per muscle pair), 0: k2_fused_* (block per muscle groups)
+    int warp_kernel;      // 2: k2u_f32 (one warp per muscle, per-instance tables), 1: k2w_f32 (one warp per muscle
+                          // pair), 0: k2_fused_* (block per muscle groups)
 };
 
 
@@ -712,6 +718,19 @@ static int fused_geometry(const MbConfig& c, int64_t M, int32_t n, int32_t K, in
     const bool f32 = c.precision == MB_F32;
     const int esz = f32 ? 4 : 8;
     g->warp_kernel = 0;
+    const bool per_row = c.param_rows > 1;
+    if (per_row && c.param_rows != M) return fail(MB_EINVAL, "per-instance tables need param_rows == M");
+    if (f32 && per_row && n <= 128) {
+        // per-instance tables: one warp per muscle, pairs of units
+        g->warp_kernel = 2;
+        g->U = 1; g->q = kWarpsPerBlock; g->G = kWarpsPerBlock; g->Gp = g->G; g->T = kWTile;
+        g->ns = n; g->npg = 0; g->ptp = 0;
+        g->threads = kWarpsPerBlock * 32;
+        g->smem = kWarpsPerBlock * (kWTile * kUPitch + 2 * kWTile) * (int)sizeof(float);
+        g->blocks = (M + g->G - 1) / g->G;
+        return MB_OK;
+    }
+    if (per_row) upt = 1;                                    // block kernels: a thread's instances share one table
     if (f32 && upt == 0 && n > 32 && n <= 128 && !env_int("MB_FUSED_BLOCK", 0)) {
         // FP32 mode, 33..128 units: one warp per pair of muscles, no cross-warp reduction
         g->warp_kernel = 1;
@@ -802,7 +821,8 @@ static int step_fused_impl(const MbConfig* cfg, const void* params_dev, int64_t 
 
     K2Args a;
     memset(&a, 0, sizeof(a));
-    a.params = params_dev; a.M = M; a.n = n; a.ns = g.ns; a.q = g.q; a.K = K; a.T = g.T; a.G = g.G; a.Gp = g.Gp;
+    a.params = params_dev; a.param_stride = cfg->param_rows > 1 ? (int64_t)(f32 ? kGroupsF32 : kGroupsF64) * n : 0;
+    a.M = M; a.n = n; a.ns = g.ns; a.q = g.q; a.K = K; a.T = g.T; a.G = g.G; a.Gp = g.Gp;
     a.npg = g.npg; a.ptp = g.ptp;
     a.exc = exc_dev; a.exc_stride_k = exc_stride_k;
     if (exc_stride_k == 0) {
@@ -848,6 +868,17 @@ static int step_fused_impl(const MbConfig* cfg, const void* params_dev, int64_t 
     const int fib = cfg->fibers_kind;
     const bool forces = forces_every > 0;
     cudaStream_t st = (cudaStream_t)stream;
+    if (g.warp_kernel == 2) {
+        const int npu = (n + 63) / 64;
+#define MB_U_FORCES(FIB, CEN, NPU_)                                                             \
+    (forces ? launch_fused(k2u_f32<FIB, CEN, NPU_, true>, a, g, st) : launch_fused(k2u_f32<FIB, CEN, NPU_, false>, a, g, st))
+#define MB_U_NPU(FIB, CEN) (npu == 2 ? MB_U_FORCES(FIB, CEN, 2) : MB_U_FORCES(FIB, CEN, 1))
+#define MB_U_CEN(FIB) (cen == 0 ? MB_U_NPU(FIB, 0) : (cen == 1 ? MB_U_NPU(FIB, 1) : MB_U_NPU(FIB, 2)))
+        return fib == MB_FIBERS_POTVIN ? MB_U_CEN(MB_FIBERS_POTVIN) : MB_U_CEN(MB_FIBERS_PYMUSCLE);
+#undef MB_U_CEN
+#undef MB_U_NPU
+#undef MB_U_FORCES
+    }
     if (g.warp_kernel) {
         const int upl = (n + 31) / 32;
 #define MB_W_FORCES(FIB, CEN, UPL_)                                                             \

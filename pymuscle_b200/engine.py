@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from . import _native as nat
-from .tables import MuscleSpec, PackedRow, pack_row
+from .tables import MuscleSpec, PackedRow, pack_row, pack_rows_per_instance
 
 _PRECISIONS = {"f32": nat.MB_F32, "fp32": nat.MB_F32, "float32": nat.MB_F32, torch.float32: nat.MB_F32,
                "f64": nat.MB_F64, "fp64": nat.MB_F64, "float64": nat.MB_F64, torch.float64: nat.MB_F64}
@@ -37,11 +37,14 @@ class MuscleBatch:
                "f64" (float64 throughout; rtol 1e-9).  Recruitment masks are exact in both.
     fresh_outputs  True (default): every step returns newly allocated tensors, like the
                reference's fresh ``current_forces`` array (fibers:258); False: reuse buffers
+    row_specs  optional: one MuscleSpec PER ROW (same unit count, see
+               ``tables.pack_rows_per_instance``) -- per-instance hyper-parameters for domain
+               randomisation; ``spec`` is then ignored except as row 0's template
     """
 
     def __init__(self, spec: Union[MuscleSpec, Sequence[MuscleSpec]], batch: int,
                  device: Union[str, torch.device, None] = None, precision="f32",
-                 fresh_outputs: bool = True):
+                 fresh_outputs: bool = True, row_specs: Optional[Sequence[MuscleSpec]] = None):
         if not torch.cuda.is_available():
             raise RuntimeError("pymuscle_b200 needs a CUDA device: there is no CPU fallback")
         nat.lib()
@@ -61,7 +64,15 @@ class MuscleBatch:
             raise ValueError("batch must be positive")
         self.fresh_outputs = bool(fresh_outputs)
 
-        self.packed: PackedRow = pack_row(specs, self.precision)
+        self.per_instance = row_specs is not None
+        if self.per_instance:
+            row_specs = list(row_specs)
+            if len(row_specs) != self.rows:
+                raise ValueError(f"row_specs has {len(row_specs)} entries for a batch of {self.rows}")
+            self.uniform, specs = True, [row_specs[0]]
+            self.packed: PackedRow = pack_rows_per_instance(row_specs, self.precision)
+        else:
+            self.packed = pack_row(specs, self.precision)
         self.specs = specs
         self.cfg = self.packed.cfg
         self.S, self.L = self.packed.S, self.packed.L
@@ -70,7 +81,11 @@ class MuscleBatch:
             self._seg_off = torch.from_numpy(self.packed.seg_off).to(self.device) if self.S > 1 else None
             self._seg_div = torch.from_numpy(self.packed.seg_div).to(self.device) if self.S > 1 else None
             self._ptf = torch.from_numpy(self.packed.ptf).to(self.device)
-            self.cpf = self._ptf.repeat(self.rows, 1).contiguous()            # fibers:63
+            if self.per_instance:
+                self._ptf = self._ptf.reshape(self.rows, self.L)
+                self.cpf = self._ptf.clone()                                  # fibers:63, each row its own peaks
+            else:
+                self.cpf = self._ptf.repeat(self.rows, 1).contiguous()        # fibers:63
             self.dur = torch.zeros(self.rows, self.L, dtype=torch.float64, device=self.device)  # pool:79
             self._forces = torch.zeros(self.rows, self.L, dtype=self.dtype, device=self.device)  # fibers:90
             self._totals = torch.zeros(self.rows, self.S, dtype=self.dtype, device=self.device)
@@ -427,7 +442,7 @@ class MuscleBatch:
     # ---- state ------------------------------------------------------------------------
     def reset(self):
         """Back to the rested state (fibers:63, pool:79)."""
-        self.cpf.copy_(self._ptf.repeat(self.rows, 1))
+        self.cpf.copy_(self._ptf if self.per_instance else self._ptf.repeat(self.rows, 1))
         self.dur.zero_()
         self._forces = torch.zeros_like(self._forces)
 

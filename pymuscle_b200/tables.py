@@ -221,3 +221,39 @@ def pack_row(specs: Sequence[MuscleSpec], precision: int) -> PackedRow:
     cfg.table_props = props.value
     seg_div = np.array([float(s.output_divisor) for s in specs], dtype=np.float64)
     return PackedRow(specs, precision, cfg, blob, seg_off, seg_div, cat["ptf"])
+
+
+def pack_rows_per_instance(row_specs: Sequence[MuscleSpec], precision: int) -> PackedRow:
+    """Per-instance hyper-parameters (domain randomisation): one packed table per batch row.
+
+    Every row is one muscle of the same unit count; rows may differ in every hyper-parameter
+    that only enters the per-unit tables -- recruitment range, peak firing rates, derecruitment
+    delta, adaptation magnitude, twitch amplitudes, contraction times, fatigue / recovery rates,
+    contraction-time change ratio -- but must share the scalars a launch passes by value
+    (firing gain, minimal firing rate, adaptation time constant, maximal duration, the fatigue
+    switches, the fibers model and the input / output scaling).  Returns a PackedRow whose blob
+    holds ``len(row_specs)`` consecutive tables and whose cfg.param_rows says so."""
+    row_specs = list(row_specs)
+    if len(row_specs) < 2:
+        raise ValueError("per-instance tables need at least two rows")
+    first = row_specs[0]
+
+    def launch_scalars(s: MuscleSpec):
+        p, f = s.pool, s.fibers
+        return (s.n, p.firing_gain, p.min_firing_rate, p.adaptation_time_constant, p.max_duration, p.apply_fatigue,
+                f.apply_fatigue, f.recovery, s.input_scale, s.output_divisor)
+
+    for r, s in enumerate(row_specs[1:], 1):
+        if launch_scalars(s) != launch_scalars(first):
+            raise ValueError(f"row {r} differs from row 0 in a per-launch scalar (unit count, firing gain, minimal "
+                             "firing rate, adaptation time constant, maximal duration, switches or I/O scaling)")
+    packs = [pack_row([s], precision) for s in row_specs]
+    cfg = packs[0].cfg
+    props = cfg.table_props
+    for pk in packs[1:]:
+        props &= pk.cfg.table_props                       # a fast path must hold for every row
+    cfg.table_props = props
+    cfg.param_rows = len(row_specs)
+    blob = np.concatenate([pk.blob for pk in packs])
+    ptf = np.stack([pk.ptf for pk in packs])               # [rows, n] initial capacities
+    return PackedRow([first], precision, cfg, blob, packs[0].seg_off, packs[0].seg_div, ptf)
