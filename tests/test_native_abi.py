@@ -108,6 +108,35 @@ def test_argument_validation_without_a_gpu():
     assert rc == nat.MB_EUNSUPPORTED
     with pytest.raises(nat.UnsupportedError):
         nat.check(rc)
+    # the environment step and the fused gather validate before touching the device as well
+    rc = lib.mb_step_env(C.byref(cfg), None, 1, 120, 1, None, None, None, None, None, None, None, None, None, 0.02, None)
+    assert rc == nat.MB_EINVAL and b"mb_step_env" in lib.mb_last_error()
+    rc = lib.mb_step_fused_gather(C.byref(cfg), None, 8, 120, 10, None, 8, None, None, None, 8, None, 0, 0, 0, None, 0.02, None)
+    assert rc == nat.MB_EINVAL
+    # per-instance tables: param_rows must match the batch
+    per = nat.MbConfig()
+    C.memmove(C.byref(per), C.byref(cfg), C.sizeof(cfg))
+    per.param_rows = 5
+    rc = lib.mb_fused_geometry(C.byref(per), 6, 120, 10, 0, C.byref(mpb), C.byref(thr), C.byref(blocks), C.byref(smem))
+    assert rc == nat.MB_EINVAL and b"param_rows" in lib.mb_last_error()
+    assert lib.mb_fused_geometry(C.byref(per), 5, 120, 10, 0, C.byref(mpb), C.byref(thr), C.byref(blocks), C.byref(smem)) == 0
+    assert thr.value == 256 and mpb.value == 8                                 # k2u_f32: one warp per muscle
+
+
+def test_per_instance_packing_and_its_checks():
+    from dataclasses import replace
+    from pymuscle_b200.tables import pack_rows_per_instance
+    base = MuscleSpec.potvin(24)
+    rows = [replace(base, fibers=replace(base.fibers, max_fatigue_rate=0.02 + 0.001 * i)) for i in range(3)]
+    pk = pack_rows_per_instance(rows, nat.MB_F32)
+    one = pack_row([rows[1]], nat.MB_F32)
+    assert pk.cfg.param_rows == 3 and pk.blob.size == 3 * one.blob.size
+    assert np.array_equal(pk.blob[one.blob.size: 2 * one.blob.size], one.blob)    # table 1 is row 1's own table
+    assert pk.ptf.shape == (3, 24)
+    with pytest.raises(ValueError, match="per-launch scalar"):
+        pack_rows_per_instance([rows[0], replace(rows[1], pool=replace(rows[1].pool, min_firing_rate=9))], nat.MB_F32)
+    with pytest.raises(ValueError):
+        pack_rows_per_instance(rows[:1], nat.MB_F32)
 
 
 def test_fused_geometry_for_the_headline_config():
