@@ -60,7 +60,7 @@ struct K1sArgs {
 // one unit, one step; state in, state out (no memory access)
 template <bool CENTRAL, bool RECOVERY>
 __device__ __forceinline__ float k1s_unit(const K1sArgs<float>& a, const UnitF& p, float x, double c, double d,
-                                          double fatdt, double rdidt, double ptf, double& cn, double& dn) {
+                                          double fatdt, double rdidt, double ptf, double& cn, double& dn, const double*) {
     bool on;
     float r = pool_rate_raw(p, a.sc, x, on);
     r = on ? r : 0.0f;                                                  // pool:171-172
@@ -76,7 +76,8 @@ __device__ __forceinline__ float k1s_unit(const K1sArgs<float>& a, const UnitF& 
 }
 template <bool CENTRAL, bool RECOVERY>
 __device__ __forceinline__ double k1s_unit(const K1sArgs<double>& a, const UnitD& p, double x, double c, double d,
-                                           double fatdt, double rdidt, double ptf, double& cn, double& dn) {
+                                           double fatdt, double rdidt, double ptf, double& cn, double& dn,
+                                           const double* exp_tab) {
     bool on;
     const double r = pool_rate(p, a.sc, x, on);
     double fr = r;
@@ -118,6 +119,8 @@ __global__ void __launch_bounds__(288, 2) k1_stream(const K1sArgs<T> a) {
     }
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ double exp2_tab[32];                       // exp_neg_fast's table (FP64 mode)
+    if (sizeof(T) == 8 && tid < 32) exp2_tab[tid] = kExp2Tab[tid];
     const int ncons = blockDim.x - 32;                    // consumer threads (== W)
     const int ncw = ncons >> 5;
     if (tid == 0) {
@@ -220,7 +223,7 @@ __global__ void __launch_bounds__(288, 2) k1_stream(const K1sArgs<T> a) {
                 double* dp = CENTRAL ? a.dur + i0 : nullptr;
                 auto row = [&](int r) {
                     double cn, dn = d[r];
-                    const T F = k1s_unit<CENTRAL, RECOVERY>(a, p, xm[r], c[r], d[r], fatdt, rdidt, ptf, cn, dn);
+                    const T F = k1s_unit<CENTRAL, RECOVERY>(a, p, xm[r], c[r], d[r], fatdt, rdidt, ptf, cn, dn, exp2_tab);
                     if (FORCES) *fp = F;
                     *cp = cn;
                     if (CENTRAL) *dp = dn;

@@ -566,11 +566,18 @@ static int launch_k1(const MbConfig& c, const void* params, int64_t rows, int64_
 template <typename T, bool CENTRAL, bool RECOVERY, bool FORCES, bool FATIGUE>
 static int launch_k1s_variant(const K1sArgs<T>& a, int threads, int smem, int64_t items, cudaStream_t st) {
     auto kern = k1_stream<T, CENTRAL, RECOVERY, FORCES, FATIGUE>;
-    if (smem > 48 * 1024) MB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    // persistent grid: exactly the blocks that are resident at once, each walking the work list
-    int per_sm = 0;
-    MB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
-    if (per_sm < 1) return fail(MB_ECUDA, "k1_stream does not fit on an SM (threads %d, smem %d)", threads, smem);
+    // persistent grid: exactly the blocks that are resident at once, each walking the work list.
+    // The opt-in and the occupancy query are cached per (instantiation, geometry): a batch-of-1 drop-in
+    // step is only ~20 us long, so two driver calls per launch would show.
+    static thread_local int c_threads = -1, c_smem = -1, c_per_sm = 0;
+    if (c_threads != threads || c_smem != smem) {
+        if (smem > 48 * 1024) MB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        int q = 0;
+        MB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, threads, smem));
+        if (q < 1) return fail(MB_ECUDA, "k1_stream does not fit on an SM (threads %d, smem %d)", threads, smem);
+        c_threads = threads; c_smem = smem; c_per_sm = q;
+    }
+    int per_sm = c_per_sm;
     const int cap = env_int("MB_K1_BPS", 0);
     if (cap > 0 && per_sm > cap) per_sm = cap;
     int64_t blocks = (int64_t)sm_count() * per_sm;
