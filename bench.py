@@ -413,7 +413,7 @@ def main():
     ap.add_argument("--muscles", type=int, default=65536)
     ap.add_argument("--window", type=int, default=1000)
     ap.add_argument("--units-per-thread", type=int, default=0)
-    ap.add_argument("--chunk", type=int, default=104, help="sub-window length of the host-buffer pipeline")
+    ap.add_argument("--chunk", type=int, default=256, help="sub-window length of the host-buffer pipeline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-k1", action="store_true")

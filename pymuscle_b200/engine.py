@@ -360,7 +360,7 @@ class MuscleBatch:
 
     # ---- K2 with host buffers: H2D / compute / D2H pipelined over sub-windows ---------
     def step_many_host(self, exc_host: torch.Tensor, step_size: float, out_host: torch.Tensor,
-                       chunk: int = 104, overlap_calls: bool = False) -> torch.Tensor:
+                       chunk: int = 256, overlap_calls: bool = False) -> torch.Tensor:
         """``step_many`` for excitations and totals that live in (pinned) HOST memory.
 
         The window is cut into sub-windows of ``chunk`` steps; the host->device copy of
