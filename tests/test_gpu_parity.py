@@ -355,3 +355,31 @@ def test_full_size_properties_config4_shard(cuda_device):
     close(b.cpf[:16].cpu().numpy(), ora.cpf, "f64", ora.t.ptf, "sampled capacities")
     np.testing.assert_allclose(b.dur[:16].cpu().numpy(), ora.dur, rtol=1e-9, atol=1e-12)
     assert bool((b.cpf <= torch.from_numpy(ora.t.ptf).to(cuda_device)[None]).all())
+
+
+@pytest.mark.parametrize("overlap", [False, True])
+def test_host_pipeline_matches_the_device_path(cuda_device, overlap):
+    """step_many_host (pinned host buffers in / out, H2D / kernel / D2H pipelined over sub-windows) is
+    what bench.py's end-to-end leg times: it must return exactly what step_many returns, window
+    after window, with and without cross-call overlap, for chunk sizes that do not divide K."""
+    M, n, K, dt = 300, 120, 200, 0.02
+    rng = np.random.default_rng(8)
+    a = MuscleBatch(MuscleSpec.potvin(n), M, cuda_device, "f32", fresh_outputs=False)
+    b = MuscleBatch(MuscleSpec.potvin(n), M, cuda_device, "f32", fresh_outputs=False)
+    out_h = [torch.empty(K, M).pin_memory() for _ in range(3)]
+    excs = [torch.from_numpy((67.0 * rng.random((K, M))).astype(np.float32)).pin_memory() for _ in range(3)]
+    for w in range(3):
+        a.step_many_host(excs[w], dt, out_h[w], chunk=72, overlap_calls=overlap)
+    a.host_pipeline_join()
+    torch.cuda.synchronize()
+    for w in range(3):
+        # same sub-window partition on the device path: bitwise equal (FP32-mode rounding depends on
+        # where a launch ends, because the state goes back to float64 there)
+        x = excs[w].to(cuda_device)
+        want = torch.cat([b.step_many(x[k0:k0 + 72], dt) for k0 in range(0, K, 72)])
+        assert torch.equal(out_h[w], want.cpu()), f"window {w}"
+    assert torch.equal(a.cpf, b.cpf) and torch.equal(a.dur, b.dur)
+    # and against one undivided launch: within the FP32-mode bar
+    c = MuscleBatch(MuscleSpec.potvin(n), M, cuda_device, "f32", fresh_outputs=False)
+    whole = c.step_many(excs[0].to(cuda_device), dt)
+    close(out_h[0].numpy(), whole.double().cpu().numpy(), "f32", 2609.03, "sub-windows vs one window")
