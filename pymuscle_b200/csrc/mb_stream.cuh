@@ -45,7 +45,8 @@ struct K1sArgs {
     const int32_t* seg_off;
     const double* seg_div;
     int32_t peripheral;
-    const T* in;                 // [rows, S]
+    const T* in;                 // [rows, S] one input per muscle, or [rows, L] one per unit (in_per_unit)
+    int32_t in_per_unit;         // 1: the ndarray form of Muscle.step (muscle.py:67, :89): staged like the state rows
     double* cpf;
     double* dur;
     T* forces;                   // may be NULL
@@ -103,7 +104,10 @@ __global__ void __launch_bounds__(288, 2) k1_stream(const K1sArgs<T> a) {
     double* cpf_s = (double*)(smem_raw + 128);            // [NS][R][rowp]
     double* dur_s = cpf_s + (size_t)NS * R * rowp;        // [NS][R][rowp]   (CENTRAL only)
     P* par_s = (P*)(CENTRAL ? dur_s + (size_t)NS * R * rowp : dur_s);     // [NS][G][W] staged unit parameters
-    T* red0 = (T*)(par_s + (size_t)NS * G * W);           // [2 item parities][2R][8]: force sums | capacity sums
+    constexpr int kInAlign = 16 / (int)sizeof(T);         // input elements per 16 bytes (bulk-copy granularity)
+    const int rowpi = W + 2 * kInAlign;                   // input row pitch (shift + round-up slack), a multiple of kInAlign
+    T* in_s = (T*)(par_s + (size_t)NS * G * W);           // [NS][R][rowpi] staged per-unit inputs (in_per_unit only)
+    T* red0 = in_s + (a.in_per_unit ? (size_t)NS * R * rowpi : 0);        // [2 item parities][2R][8]: force | capacity sums
     // ragged rows: segment offsets and divisors are read once per work item by every thread ->
     // keep them in shared memory instead of paying a dependent global load per item
     double* segdiv_s = (double*)(red0 + 2 * 2 * R * 8);   // [S]
@@ -153,13 +157,21 @@ __global__ void __launch_bounds__(288, 2) k1_stream(const K1sArgs<T> a) {
                 const int64_t a0 = e0 & ~(int64_t)1, a1 = (e0 + count + 1) & ~(int64_t)1;
                 const uint32_t bytes = (uint32_t)(a1 - a0) * 8u;
                 const uint32_t pbytes = (uint32_t)count * 16u;           // one parameter group of the tile
-                if (lane == 0) mbar_expect_tx(bar0 + 8u * s, bytes * nrows * (CENTRAL ? 2u : 1u) + pbytes * G);
+                const int64_t i0a = e0 & ~(int64_t)(kInAlign - 1);       // per-unit inputs: 16-byte aligned span of the tile
+                const int64_t i1a = (e0 + count + kInAlign - 1) & ~(int64_t)(kInAlign - 1);
+                const uint32_t ibytes = a.in_per_unit ? (uint32_t)(i1a - i0a) * (uint32_t)sizeof(T) : 0u;
+                if (lane == 0)
+                    mbar_expect_tx(bar0 + 8u * s, bytes * nrows * (CENTRAL ? 2u : 1u) + pbytes * G + ibytes * nrows);
                 __syncwarp();
                 if (lane < nrows) {
                     const int64_t g = (r0 + lane) * a.L + a0;
                     const uint32_t so = (uint32_t)((s * R + lane) * rowp) * 8u;
                     bulk_g2s(smem_u32(cpf_s) + so, a.cpf + g, bytes, bar0 + 8u * s);
                     if (CENTRAL) bulk_g2s(smem_u32(dur_s) + so, a.dur + g, bytes, bar0 + 8u * s);
+                }
+                if (a.in_per_unit && lane >= 16 && lane < 16 + nrows) {  // lanes 16 .. 16+R-1: the input rows
+                    const int r = lane - 16;
+                    bulk_g2s(smem_u32(in_s + (size_t)(s * R + r) * rowpi), a.in + (r0 + r) * a.L + i0a, ibytes, bar0 + 8u * s);
                 }
                 if (lane >= R && lane < R + G) {
                     const int grp = lane - R;                            // lanes R .. R+G-1: the parameter groups
@@ -178,7 +190,8 @@ __global__ void __launch_bounds__(288, 2) k1_stream(const K1sArgs<T> a) {
         const int seg = (int)(item - chunk * a.S);
         const int64_t r0 = chunk * R;
 #pragma unroll
-        for (int r = 0; r < R; ++r) x[r] = (item < items && r0 + r < a.rows) ? a.in[(r0 + r) * a.S + seg] : T(0);
+        for (int r = 0; r < R; ++r)
+            x[r] = (!a.in_per_unit && item < items && r0 + r < a.rows) ? a.in[(r0 + r) * a.S + seg] : T(0);
     };
     uint32_t it = 0, item_no = 0;
     T xnext[R];
@@ -216,6 +229,11 @@ __global__ void __launch_bounds__(288, 2) k1_stream(const K1sArgs<T> a) {
                 for (int r = 0; r < R; ++r) {
                     c[r] = cs[r * rowp];
                     d[r] = CENTRAL ? ds[r * rowp] : 0.0;
+                }
+                if (a.in_per_unit) {                                 // this unit's own excitation in every row
+                    const T* xs = in_s + (size_t)(s * R) * rowpi + ((off0 + u0) & (kInAlign - 1)) + tid;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) xm[r] = xs[r * rowpi];
                 }
                 const int64_t i0 = r0 * a.L + off0 + u;
                 T* fp = FORCES ? a.forces + i0 : nullptr;

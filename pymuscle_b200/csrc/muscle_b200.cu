@@ -590,10 +590,19 @@ static int launch_k1s_variant(const K1sArgs<T>& a, int threads, int smem, int64_
 // The streaming kernel covers the batched hot case: whole-muscle stage, one input per muscle,
 // no mask / rate outputs, even row length, 16-byte aligned state arrays.
 template <typename T>
-static bool k1s_eligible(const MbConfig& c, int64_t L, int32_t stage, int32_t in_per_unit, const double* cpf,
-                         const double* dur, const uint8_t* mask, const void* rates) {
+static bool k1s_eligible(const MbConfig& c, int64_t L, int32_t stage, int32_t in_per_unit, const void* in,
+                         const double* cpf, const double* dur, const uint8_t* mask, const void* rates) {
     if (env_int("MB_K1_GENERIC", 0) || c.param_rows > 1) return false;       // per-instance tables: generic kernel
-    if (stage != MB_STAGE_MUSCLE || in_per_unit || mask || rates || !c.peripheral_fatigue) return false;
+    if (stage != MB_STAGE_MUSCLE || mask || rates || !c.peripheral_fatigue) return false;
+    // per-unit inputs are staged with bulk copies too: rows must start on 16-byte boundaries
+    if (in_per_unit) {
+        if (L % (16 / (int)sizeof(T)) != 0 || ((uintptr_t)in % 16) != 0) return false;
+        cudaPointerAttributes at;                             // (the drop-in classes pass pinned HOST memory)
+        if (cudaPointerGetAttributes(&at, in) != cudaSuccess || at.type != cudaMemoryTypeDevice) {
+            cudaGetLastError();
+            return false;
+        }
+    }
     if (L % 2 != 0 || ((uintptr_t)cpf % 16) != 0) return false;
     if (c.central_fatigue && ((uintptr_t)dur % 16) != 0) return false;
     return true;
@@ -601,14 +610,14 @@ static bool k1s_eligible(const MbConfig& c, int64_t L, int32_t stage, int32_t in
 
 template <typename T>
 static int launch_k1s(const MbConfig& c, const void* params, int64_t rows, int64_t L, int32_t S,
-                      const int32_t* seg_off, const double* seg_div, const void* in, double* cpf, double* dur,
-                      void* forces, void* totals, const void* out_gain, double* fatigue, double dt, cudaStream_t st,
-                      const typename Vec<T>::S& sc) {
+                      const int32_t* seg_off, const double* seg_div, const void* in, int32_t in_per_unit, double* cpf,
+                      double* dur, void* forces, void* totals, const void* out_gain, double* fatigue, double dt,
+                      cudaStream_t st, const typename Vec<T>::S& sc) {
     K1sArgs<T> a;
     a.params = (const typename StreamTraits<T>::P*)params;
     a.rows = rows; a.L = L; a.S = S; a.seg_off = seg_off; a.seg_div = seg_div;
     a.peripheral = c.peripheral_fatigue != 0;
-    a.in = (const T*)in; a.cpf = cpf; a.dur = dur; a.forces = (T*)forces; a.totals = (T*)totals;
+    a.in = (const T*)in; a.in_per_unit = in_per_unit; a.cpf = cpf; a.dur = dur; a.forces = (T*)forces; a.totals = (T*)totals;
     a.out_gain = (const T*)out_gain; a.fatigue = fatigue; a.fat_div = c.output_divisor;
     a.dt = dt;
     a.adk_d = -kLog2e / c.adaptation_time_constant;
@@ -620,7 +629,8 @@ static int launch_k1s(const MbConfig& c, const void* params, int64_t rows, int64
     const int wmax = env_int("MB_K1_W", 256);
     if (W > wmax) W = wmax;
     if (W < 32) W = 32;
-    const int stage_bytes = kStreamRows * (W + 2) * 8 * (central ? 2 : 1) + StreamTraits<T>::G * W * 16;   // state rows + unit parameters
+    const int stage_bytes = kStreamRows * (W + 2) * 8 * (central ? 2 : 1) + StreamTraits<T>::G * W * 16 +   // state rows + unit parameters
+                            (in_per_unit ? kStreamRows * (W + 2 * (16 / (int)sizeof(T))) * (int)sizeof(T) : 0);   // + per-unit inputs
     int NS = env_int("MB_K1_STAGES", 0);
     if (NS <= 0) NS = 2;                                      // measured: double buffering x 2+ blocks/SM saturates HBM; deeper rings only cost occupancy
     if (NS > 8) NS = 8;
@@ -655,15 +665,15 @@ extern "C" int mb_step(const MbConfig* cfg, const void* params_dev, int64_t rows
         return fail(MB_EINVAL, "mb_step: per-instance tables need a uniform batch with param_rows == rows");
     cudaStream_t st = (cudaStream_t)stream;
     if (cfg->precision == MB_F32) {
-        if (k1s_eligible<float>(*cfg, L, stage, in_per_unit, cpf_dev, dur_dev, mask_dev, rates_dev))
-            return launch_k1s<float>(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, in_dev, cpf_dev, dur_dev,
-                                     forces_dev, totals_dev, nullptr, nullptr, step_size, st, scal_f(*cfg));
+        if (k1s_eligible<float>(*cfg, L, stage, in_per_unit, in_dev, cpf_dev, dur_dev, mask_dev, rates_dev))
+            return launch_k1s<float>(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, in_dev, in_per_unit, cpf_dev,
+                                     dur_dev, forces_dev, totals_dev, nullptr, nullptr, step_size, st, scal_f(*cfg));
         return launch_k1<float>(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, stage, in_dev, in_per_unit, cpf_dev,
                                 dur_dev, forces_dev, totals_dev, mask_dev, rates_dev, step_size, st, scal_f(*cfg));
     }
-    if (k1s_eligible<double>(*cfg, L, stage, in_per_unit, cpf_dev, dur_dev, mask_dev, rates_dev))
-        return launch_k1s<double>(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, in_dev, cpf_dev, dur_dev,
-                                  forces_dev, totals_dev, nullptr, nullptr, step_size, st, scal_d(*cfg));
+    if (k1s_eligible<double>(*cfg, L, stage, in_per_unit, in_dev, cpf_dev, dur_dev, mask_dev, rates_dev))
+        return launch_k1s<double>(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, in_dev, in_per_unit, cpf_dev,
+                                  dur_dev, forces_dev, totals_dev, nullptr, nullptr, step_size, st, scal_d(*cfg));
     return launch_k1<double>(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, stage, in_dev, in_per_unit, cpf_dev, dur_dev,
                              forces_dev, totals_dev, mask_dev, rates_dev, step_size, st, scal_d(*cfg));
 }
@@ -681,14 +691,14 @@ extern "C" int mb_step_env(const MbConfig* cfg, const void* params_dev, int64_t 
     if (cfg->central_fatigue && !dur_dev) return fail(MB_EINVAL, "mb_step_env: dur is NULL");
     cudaStream_t st = (cudaStream_t)stream;
     if (cfg->precision == MB_F32) {
-        if (!k1s_eligible<float>(*cfg, L, MB_STAGE_MUSCLE, 0, cpf_dev, dur_dev, nullptr, nullptr))
+        if (!k1s_eligible<float>(*cfg, L, MB_STAGE_MUSCLE, 0, in_dev, cpf_dev, dur_dev, nullptr, nullptr))
             return fail(MB_EUNSUPPORTED, "mb_step_env needs an even row length, 16-byte aligned state and peripheral fatigue on");
-        return launch_k1s<float>(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, in_dev, cpf_dev, dur_dev,
+        return launch_k1s<float>(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, in_dev, 0, cpf_dev, dur_dev,
                                  forces_dev, totals_dev, out_gain_dev, fatigue_dev, step_size, st, scal_f(*cfg));
     }
-    if (!k1s_eligible<double>(*cfg, L, MB_STAGE_MUSCLE, 0, cpf_dev, dur_dev, nullptr, nullptr))
+    if (!k1s_eligible<double>(*cfg, L, MB_STAGE_MUSCLE, 0, in_dev, cpf_dev, dur_dev, nullptr, nullptr))
         return fail(MB_EUNSUPPORTED, "mb_step_env needs an even row length, 16-byte aligned state and peripheral fatigue on");
-    return launch_k1s<double>(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, in_dev, cpf_dev, dur_dev,
+    return launch_k1s<double>(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, in_dev, 0, cpf_dev, dur_dev,
                               forces_dev, totals_dev, out_gain_dev, fatigue_dev, step_size, st, scal_d(*cfg));
 }
 
