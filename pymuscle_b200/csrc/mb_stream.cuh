@@ -39,6 +39,7 @@ template <> struct StreamTraits<double> { using U = UnitD; using P = double2; us
 template <typename T>
 struct K1sArgs {
     const typename StreamTraits<T>::P* params;
+    int64_t param_stride;        // 0: one shared table; else vectors between the tables of consecutive rows (per-instance)
     int64_t rows, L;
     int32_t S, W, NS;
     int32_t seg_in_smem;         // 1: seg_off / seg_div are copied to shared memory at kernel start
@@ -92,7 +93,7 @@ __device__ __forceinline__ double k1s_unit(const K1sArgs<double>& a, const UnitD
     return F;
 }
 
-template <typename T, bool CENTRAL, bool RECOVERY, bool FORCES, bool FATIGUE>
+template <typename T, bool CENTRAL, bool RECOVERY, bool FORCES, bool FATIGUE, bool PERROW = false>
 __global__ void __launch_bounds__(288, 2) k1_stream(const K1sArgs<T> a) {
     constexpr int R = kStreamRows;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -103,10 +104,11 @@ __global__ void __launch_bounds__(288, 2) k1_stream(const K1sArgs<T> a) {
     constexpr int G = StreamTraits<T>::G;
     double* cpf_s = (double*)(smem_raw + 128);            // [NS][R][rowp]
     double* dur_s = cpf_s + (size_t)NS * R * rowp;        // [NS][R][rowp]   (CENTRAL only)
-    P* par_s = (P*)(CENTRAL ? dur_s + (size_t)NS * R * rowp : dur_s);     // [NS][G][W] staged unit parameters
+    P* par_s = (P*)(CENTRAL ? dur_s + (size_t)NS * R * rowp : dur_s);     // [NS][PR][G][W] staged unit parameters
     constexpr int kInAlign = 16 / (int)sizeof(T);         // input elements per 16 bytes (bulk-copy granularity)
     const int rowpi = W + 2 * kInAlign;                   // input row pitch (shift + round-up slack), a multiple of kInAlign
-    T* in_s = (T*)(par_s + (size_t)NS * G * W);           // [NS][R][rowpi] staged per-unit inputs (in_per_unit only)
+    constexpr int PR = PERROW ? R : 1;                    // parameter tiles per stage: one, or one per row (per-instance tables)
+    T* in_s = (T*)(par_s + (size_t)NS * PR * G * W);      // [NS][R][rowpi] staged per-unit inputs (in_per_unit only)
     T* red0 = in_s + (a.in_per_unit ? (size_t)NS * R * rowpi : 0);        // [2 item parities][2R][8]: force | capacity sums
     // ragged rows: segment offsets and divisors are read once per work item by every thread ->
     // keep them in shared memory instead of paying a dependent global load per item
@@ -160,8 +162,10 @@ __global__ void __launch_bounds__(288, 2) k1_stream(const K1sArgs<T> a) {
                 const int64_t i0a = e0 & ~(int64_t)(kInAlign - 1);       // per-unit inputs: 16-byte aligned span of the tile
                 const int64_t i1a = (e0 + count + kInAlign - 1) & ~(int64_t)(kInAlign - 1);
                 const uint32_t ibytes = a.in_per_unit ? (uint32_t)(i1a - i0a) * (uint32_t)sizeof(T) : 0u;
+                const uint32_t ptiles = PERROW ? (uint32_t)nrows : 1u;
                 if (lane == 0)
-                    mbar_expect_tx(bar0 + 8u * s, bytes * nrows * (CENTRAL ? 2u : 1u) + pbytes * G + ibytes * nrows);
+                    mbar_expect_tx(bar0 + 8u * s,
+                                   bytes * nrows * (CENTRAL ? 2u : 1u) + pbytes * G * ptiles + ibytes * nrows);
                 __syncwarp();
                 if (lane < nrows) {
                     const int64_t g = (r0 + lane) * a.L + a0;
@@ -173,10 +177,19 @@ __global__ void __launch_bounds__(288, 2) k1_stream(const K1sArgs<T> a) {
                     const int r = lane - 16;
                     bulk_g2s(smem_u32(in_s + (size_t)(s * R + r) * rowpi), a.in + (r0 + r) * a.L + i0a, ibytes, bar0 + 8u * s);
                 }
-                if (lane >= R && lane < R + G) {
-                    const int grp = lane - R;                            // lanes R .. R+G-1: the parameter groups
-                    bulk_g2s(smem_u32(par_s + (size_t)(s * G + grp) * W), a.params + (int64_t)grp * a.L + e0, pbytes,
-                             bar0 + 8u * s);
+                if (!PERROW) {
+                    if (lane >= R && lane < R + G) {
+                        const int grp = lane - R;                        // lanes R .. R+G-1: the parameter groups
+                        bulk_g2s(smem_u32(par_s + (size_t)(s * G + grp) * W), a.params + (int64_t)grp * a.L + e0, pbytes,
+                                 bar0 + 8u * s);
+                    }
+                } else {
+                    // per-instance tables: one tile per (row, group), spread over the 32 lanes
+                    for (int j = lane; j < nrows * G; j += 32) {
+                        const int r = j / G, grp = j - r * G;
+                        bulk_g2s(smem_u32(par_s + (size_t)((s * R + r) * G + grp) * W),
+                                 a.params + (r0 + r) * a.param_stride + (int64_t)grp * a.L + e0, pbytes, bar0 + 8u * s);
+                    }
                 }
             }
         }
@@ -219,9 +232,10 @@ __global__ void __launch_bounds__(288, 2) k1_stream(const K1sArgs<T> a) {
             const int shift = (off0 + u0) & 1;
             mbar_wait(bar0 + 8u * s, ph);
             if (active) {
-                const auto p = load_unit_staged(par_s + (size_t)(s * G) * W, W, tid);
-                const double fatdt = (double)p.fat * a.dt, rdidt = (double)p.rdi * a.dt;
-                const double ptf = unit_peak(p);
+                const P* pst = par_s + (size_t)(s * PR * G) * W;
+                auto p = load_unit_staged(pst, W, tid);
+                double fatdt = (double)p.fat * a.dt, rdidt = (double)p.rdi * a.dt;
+                double ptf = unit_peak(p);
                 const double* cs = cpf_s + (s * R) * rowp + shift + tid;
                 const double* ds = dur_s + (s * R) * rowp + shift + tid;
                 double c[R], d[R];
@@ -240,6 +254,12 @@ __global__ void __launch_bounds__(288, 2) k1_stream(const K1sArgs<T> a) {
                 double* cp = a.cpf + i0;
                 double* dp = CENTRAL ? a.dur + i0 : nullptr;
                 auto row = [&](int r) {
+                    if (PERROW && r > 0) {                           // per-instance tables: this row's own parameters
+                        p = load_unit_staged(pst + (size_t)(r * G) * W, W, tid);
+                        fatdt = (double)p.fat * a.dt;
+                        rdidt = (double)p.rdi * a.dt;
+                        ptf = unit_peak(p);
+                    }
                     double cn, dn = d[r];
                     const T F = k1s_unit<CENTRAL, RECOVERY>(a, p, xm[r], c[r], d[r], fatdt, rdidt, ptf, cn, dn, exp2_tab);
                     if (FORCES) *fp = F;

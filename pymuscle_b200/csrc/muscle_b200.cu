@@ -563,9 +563,9 @@ static int launch_k1(const MbConfig& c, const void* params, int64_t rows, int64_
 }
 
 // ---- K1s launcher ---------------------------------------------------------------------------
-template <typename T, bool CENTRAL, bool RECOVERY, bool FORCES, bool FATIGUE>
+template <typename T, bool CENTRAL, bool RECOVERY, bool FORCES, bool FATIGUE, bool PERROW = false>
 static int launch_k1s_variant(const K1sArgs<T>& a, int threads, int smem, int64_t items, cudaStream_t st) {
-    auto kern = k1_stream<T, CENTRAL, RECOVERY, FORCES, FATIGUE>;
+    auto kern = k1_stream<T, CENTRAL, RECOVERY, FORCES, FATIGUE, PERROW>;
     // persistent grid: exactly the blocks that are resident at once, each walking the work list.
     // The opt-in and the occupancy query are cached per (instantiation, geometry): a batch-of-1 drop-in
     // step is only ~20 us long, so two driver calls per launch would show.
@@ -591,8 +591,11 @@ static int launch_k1s_variant(const K1sArgs<T>& a, int threads, int smem, int64_
 // no mask / rate outputs, even row length, 16-byte aligned state arrays.
 template <typename T>
 static bool k1s_eligible(const MbConfig& c, int64_t L, int32_t stage, int32_t in_per_unit, const void* in,
-                         const double* cpf, const double* dur, const uint8_t* mask, const void* rates) {
-    if (env_int("MB_K1_GENERIC", 0) || c.param_rows > 1) return false;       // per-instance tables: generic kernel
+                         const double* cpf, const double* dur, const uint8_t* mask, const void* rates,
+                         const void* forces = (const void*)1, const void* fatigue = nullptr) {
+    if (env_int("MB_K1_GENERIC", 0)) return false;
+    // per-instance tables: FP32 mode with the force output and without the fatigue epilogue (one instantiation set)
+    if (c.param_rows > 1 && (sizeof(T) != 4 || !forces || fatigue)) return false;
     if (stage != MB_STAGE_MUSCLE || mask || rates || !c.peripheral_fatigue) return false;
     // per-unit inputs are staged with bulk copies too: rows must start on 16-byte boundaries
     if (in_per_unit) {
@@ -615,6 +618,7 @@ static int launch_k1s(const MbConfig& c, const void* params, int64_t rows, int64
                       cudaStream_t st, const typename Vec<T>::S& sc) {
     K1sArgs<T> a;
     a.params = (const typename StreamTraits<T>::P*)params;
+    a.param_stride = c.param_rows > 1 ? (int64_t)StreamTraits<T>::G * L : 0;
     a.rows = rows; a.L = L; a.S = S; a.seg_off = seg_off; a.seg_div = seg_div;
     a.peripheral = c.peripheral_fatigue != 0;
     a.in = (const T*)in; a.in_per_unit = in_per_unit; a.cpf = cpf; a.dur = dur; a.forces = (T*)forces; a.totals = (T*)totals;
@@ -626,10 +630,12 @@ static int launch_k1s(const MbConfig& c, const void* params, int64_t rows, int64
     const bool central = c.central_fatigue != 0, recovery = c.fibers_kind == MB_FIBERS_PYMUSCLE;
     const int64_t mean_n = (L + S - 1) / S;
     int W = (int)((mean_n + 31) / 32) * 32;
-    const int wmax = env_int("MB_K1_W", 256);
+    // per-instance tables put R parameter tiles into every stage: narrower tiles keep two stages within reach
+    const int wmax = env_int("MB_K1_W", c.param_rows > 1 ? 64 : 256);
     if (W > wmax) W = wmax;
     if (W < 32) W = 32;
-    const int stage_bytes = kStreamRows * (W + 2) * 8 * (central ? 2 : 1) + StreamTraits<T>::G * W * 16 +   // state rows + unit parameters
+    const int stage_bytes = kStreamRows * (W + 2) * 8 * (central ? 2 : 1) +                                // state rows
+                            StreamTraits<T>::G * W * 16 * (c.param_rows > 1 ? kStreamRows : 1) +         // + unit parameters
                             (in_per_unit ? kStreamRows * (W + 2 * (16 / (int)sizeof(T))) * (int)sizeof(T) : 0);   // + per-unit inputs
     int NS = env_int("MB_K1_STAGES", 0);
     if (NS <= 0) NS = 2;                                      // measured: double buffering x 2+ blocks/SM saturates HBM; deeper rings only cost occupancy
@@ -643,6 +649,12 @@ static int launch_k1s(const MbConfig& c, const void* params, int64_t rows, int64
 #define MB_K1S_F(C_, R_, F_) (fatigue ? launch_k1s_variant<T, C_, R_, F_, true>(a, threads, smem, items, st) \
                                        : launch_k1s_variant<T, C_, R_, F_, false>(a, threads, smem, items, st))
 #define MB_K1S(C_, R_) (forces ? MB_K1S_F(C_, R_, true) : MB_K1S_F(C_, R_, false))
+    if (c.param_rows > 1) {                                   // per-instance tables: forces on, no fatigue epilogue
+        if (central) return recovery ? launch_k1s_variant<T, true, true, true, false, true>(a, threads, smem, items, st)
+                                     : launch_k1s_variant<T, true, false, true, false, true>(a, threads, smem, items, st);
+        return recovery ? launch_k1s_variant<T, false, true, true, false, true>(a, threads, smem, items, st)
+                        : launch_k1s_variant<T, false, false, true, false, true>(a, threads, smem, items, st);
+    }
     if (central) return recovery ? MB_K1S(true, true) : MB_K1S(true, false);
     return recovery ? MB_K1S(false, true) : MB_K1S(false, false);
 #undef MB_K1S_F
@@ -665,13 +677,13 @@ extern "C" int mb_step(const MbConfig* cfg, const void* params_dev, int64_t rows
         return fail(MB_EINVAL, "mb_step: per-instance tables need a uniform batch with param_rows == rows");
     cudaStream_t st = (cudaStream_t)stream;
     if (cfg->precision == MB_F32) {
-        if (k1s_eligible<float>(*cfg, L, stage, in_per_unit, in_dev, cpf_dev, dur_dev, mask_dev, rates_dev))
+        if (k1s_eligible<float>(*cfg, L, stage, in_per_unit, in_dev, cpf_dev, dur_dev, mask_dev, rates_dev, forces_dev))
             return launch_k1s<float>(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, in_dev, in_per_unit, cpf_dev,
                                      dur_dev, forces_dev, totals_dev, nullptr, nullptr, step_size, st, scal_f(*cfg));
         return launch_k1<float>(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, stage, in_dev, in_per_unit, cpf_dev,
                                 dur_dev, forces_dev, totals_dev, mask_dev, rates_dev, step_size, st, scal_f(*cfg));
     }
-    if (k1s_eligible<double>(*cfg, L, stage, in_per_unit, in_dev, cpf_dev, dur_dev, mask_dev, rates_dev))
+    if (k1s_eligible<double>(*cfg, L, stage, in_per_unit, in_dev, cpf_dev, dur_dev, mask_dev, rates_dev, forces_dev))
         return launch_k1s<double>(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, in_dev, in_per_unit, cpf_dev,
                                   dur_dev, forces_dev, totals_dev, nullptr, nullptr, step_size, st, scal_d(*cfg));
     return launch_k1<double>(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, stage, in_dev, in_per_unit, cpf_dev, dur_dev,
@@ -691,12 +703,12 @@ extern "C" int mb_step_env(const MbConfig* cfg, const void* params_dev, int64_t 
     if (cfg->central_fatigue && !dur_dev) return fail(MB_EINVAL, "mb_step_env: dur is NULL");
     cudaStream_t st = (cudaStream_t)stream;
     if (cfg->precision == MB_F32) {
-        if (!k1s_eligible<float>(*cfg, L, MB_STAGE_MUSCLE, 0, in_dev, cpf_dev, dur_dev, nullptr, nullptr))
+        if (!k1s_eligible<float>(*cfg, L, MB_STAGE_MUSCLE, 0, in_dev, cpf_dev, dur_dev, nullptr, nullptr, forces_dev, fatigue_dev))
             return fail(MB_EUNSUPPORTED, "mb_step_env needs an even row length, 16-byte aligned state and peripheral fatigue on");
         return launch_k1s<float>(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, in_dev, 0, cpf_dev, dur_dev,
                                  forces_dev, totals_dev, out_gain_dev, fatigue_dev, step_size, st, scal_f(*cfg));
     }
-    if (!k1s_eligible<double>(*cfg, L, MB_STAGE_MUSCLE, 0, in_dev, cpf_dev, dur_dev, nullptr, nullptr))
+    if (!k1s_eligible<double>(*cfg, L, MB_STAGE_MUSCLE, 0, in_dev, cpf_dev, dur_dev, nullptr, nullptr, forces_dev, fatigue_dev))
         return fail(MB_EUNSUPPORTED, "mb_step_env needs an even row length, 16-byte aligned state and peripheral fatigue on");
     return launch_k1s<double>(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, in_dev, 0, cpf_dev, dur_dev,
                               forces_dev, totals_dev, out_gain_dev, fatigue_dev, step_size, st, scal_d(*cfg));
