@@ -69,7 +69,6 @@ __device__ __forceinline__ UnitD load_unit_staged(const double2* P, int W, int i
 // Scalars derived from MbConfig by the launcher (host, float64) -- passed by value.
 struct ScalF {
     float gain_e;     // firing_gain * input_scale
-    float adk;        // -log2(e) / tau            : exp(-dur/tau) = ex2(dur * adk)
     float argmin;     // -max_duration*log2(e)/tau : lower bound of the exponent
     float c25k;       // ((1 - exp(-2*0.4^3)) / 0.4) / kappa      (fibers:240-241)
     float ythr;       // 0.4 * kappa                               (fibers:233-236)

@@ -58,7 +58,6 @@ static const double kLinScale = 1.0 - std::exp(-2.0 * (0.4 * 0.4 * 0.4));   // f
 static ScalF scal_f(const MbConfig& c) {
     ScalF s;
     s.gain_e = (float)(c.firing_gain * c.input_scale);
-    s.adk = (float)(-kLog2e / c.adaptation_time_constant);
     s.argmin = (float)(-c.max_duration * kLog2e / c.adaptation_time_constant);
     s.c25k = (float)(kLinScale / 0.4 / kKappa);
     s.ythr = (float)(0.4 * kKappa);

@@ -186,7 +186,6 @@ class MuscleBatch:
                      forces=mk(self.rows, self.L))
             h["x_np"], h["xu_np"] = h["x"].numpy(), h["xu"].numpy()
             h["out_np"], h["forces_np"] = h["out"].numpy(), h["forces"].numpy()
-            h["stream"] = torch.cuda.current_stream(self.device)
             h["npdt"] = npdt
             self._hostio = h
         if isinstance(excitation, (int, float)):
@@ -224,7 +223,6 @@ class MuscleBatch:
             nat.check(rc)
         self.launches += 1
         st.synchronize()
-        self._forces_on_host = True
         return h["out_np"]
 
     def host_forces(self) -> np.ndarray:
