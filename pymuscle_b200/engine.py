@@ -48,6 +48,8 @@ class MuscleBatch:
         if not torch.cuda.is_available():
             raise RuntimeError("pymuscle_b200 needs a CUDA device: there is no CPU fallback")
         nat.lib()
+        self._ctor = dict(spec=spec, batch=batch, device=device, precision=precision, fresh_outputs=fresh_outputs,
+                          row_specs=row_specs)
         self.uniform = isinstance(spec, MuscleSpec)
         specs = [spec] if self.uniform else list(spec)
         if precision not in _PRECISIONS:
@@ -449,6 +451,22 @@ class MuscleBatch:
                                                   int(units_per_thread), C.byref(mpb), C.byref(thr),
                                                   C.byref(blocks), C.byref(smem)))
         return dict(muscles_per_block=mpb.value, threads=thr.value, blocks=blocks.value, smem_bytes=smem.value)
+
+    # ---- copying / pickling (the reference's objects are plain Python and can be copied) -------
+    def __getstate__(self):
+        ctor = dict(self._ctor)
+        ctor["device"] = str(self.device)
+        if isinstance(ctor["precision"], torch.dtype):
+            ctor["precision"] = "f32" if ctor["precision"] == torch.float32 else "f64"
+        return {"ctor": ctor, "cpf": self.cpf.cpu(), "dur": self.dur.cpu(), "forces": self._forces.cpu(),
+                "launches": self.launches}
+
+    def __setstate__(self, state):
+        self.__init__(**state["ctor"])
+        self.cpf.copy_(state["cpf"])
+        self.dur.copy_(state["dur"])
+        self._forces = state["forces"].to(self.device)
+        self.launches = state["launches"]
 
     # ---- state ------------------------------------------------------------------------
     def reset(self):

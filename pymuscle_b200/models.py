@@ -101,6 +101,12 @@ class PotvinFuglevand2017MuscleFibers(Model):
                 self._engine.current_forces[0].cpu().numpy()
         return self._forces_host
 
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        d["_forces_host"] = np.array(self.current_forces)      # materialise: the source engine does not travel
+        d["_forces_src"] = None
+        return d
+
     @property
     def current_peak_forces(self) -> np.ndarray:
         """fibers:92-94 (a host snapshot of the device state)."""

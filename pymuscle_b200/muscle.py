@@ -43,6 +43,22 @@ class Muscle(object):
         eng.cpf = self._fibers._engine.cpf
         self._engine = eng
 
+    # copying / pickling: the fused engine aliases the two models' device state, so it is rebuilt
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        d["_engine"] = d["_engine"] is not None
+        return d
+
+    def __setstate__(self, d):
+        had_engine = d.pop("_engine")
+        self.__dict__.update(d)
+        self._engine = None
+        if had_engine:
+            self._build_engine()
+            # the last step's forces travelled with the old engine's host buffer: keep a copy
+            if getattr(self._fibers, "_forces_src", None) is not None:
+                self._fibers._forces_src = None
+
     @property
     def motor_unit_count(self):
         return self._pool.motor_unit_count

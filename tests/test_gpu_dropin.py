@@ -208,3 +208,34 @@ def test_generic_composition_with_a_user_model():
     assert m.step(0.3, 1.0) == pytest.approx(2586.7530897)
     with pytest.raises(AssertionError):
         Muscle(ConstantPool(10), Fibers(120))
+
+
+def test_deepcopy_and_pickle_of_muscles():
+    """The reference's muscles are plain Python objects: environments deep-copy and pickle them.
+    A copy carries the full state and then evolves independently."""
+    import copy
+    import pickle
+    import torch
+    import pymuscle_b200 as pm
+    m = pm.StandardMuscle()
+    for _ in range(30):
+        m.step(0.7, 0.05)
+    twin = copy.deepcopy(m)
+    back = pickle.loads(pickle.dumps(m))
+    assert np.array_equal(twin.current_forces, m.current_forces)
+    assert twin.get_peripheral_fatigue() == m.get_peripheral_fatigue() == back.get_peripheral_fatigue()
+    a, b, c = m.step(0.4, 0.05), twin.step(0.4, 0.05), back.step(0.4, 0.05)
+    assert a == b == c
+    assert np.array_equal(m.current_forces, twin.current_forces)
+    twin.step(1.0, 0.05)                                           # independent from here on
+    assert m.step(0.0, 0.05) == back.step(0.0, 0.05)
+    assert twin.get_peripheral_fatigue() != m.get_peripheral_fatigue()
+    p = pm.PotvinFuglevandMuscle(60)
+    p.step(40.0, 0.1)
+    q = copy.deepcopy(p)
+    assert p.step(40.0, 0.1) == q.step(40.0, 0.1)
+    from pymuscle_b200 import MuscleBatch, MuscleSpec
+    bt = MuscleBatch(MuscleSpec.potvin(24), 5, "cuda:0", "f32")
+    bt.step(torch.full((5,), 30.0, device="cuda:0"), 0.02)
+    bt2 = copy.deepcopy(bt)
+    assert torch.equal(bt.cpf, bt2.cpf) and bt.cpf.data_ptr() != bt2.cpf.data_ptr()
