@@ -151,6 +151,8 @@ struct PairParams {            // what a step needs of the unit(s) of a pair
 struct PairState {
     float2 hi, lo, cpf, cnt, nD, room, arg0;
 };
+constexpr float kLinTop = 0.12014662085535621f;   // 1 - exp(-2 * 0.4^3): the two pieces of the force curve meet here
+
 struct PairScal {              // per-launch scalars
     float gain_e, c25k, ythr, argmin, dtk, decay, dm1;
 };
@@ -237,9 +239,11 @@ __device__ __forceinline__ float2 pair_step(PairState& st, const PairParams<PT>&
     ex.x = ex2_approx(ny3.x);
     ex.y = ex2_approx(ny3.y);
     const float2 sig = __ffma2_rn(ex, B2(-1.0f), B2(1.0f));
+    // piecewise curve without a predicate: below x = 0.4 the line lies above the sigmoid and below its
+    // value at 0.4 (kLinTop = 1 - exp(-2*0.4^3), where the pieces meet); above, the sigmoid is the larger
     float2 nf;
-    nf.x = (ny.x >= -sc.ythr) ? lin.x : sig.x;                              // x <= 0.4 (fibers:233-236)
-    nf.y = (ny.y >= -sc.ythr) ? lin.y : sig.y;
+    nf.x = fmaxf(fminf(lin.x, kLinTop), sig.x);                             // fibers:233-246
+    nf.y = fmaxf(fminf(lin.y, kLinTop), sig.y);
     const float2 F = __fmul2_rn(nf, st.cpf);                                // fibers:258 (capacity BEFORE the update)
     // ---- capacity update on the compensated pair (fibers:110-114, pmf:94-105) ----
     float2 l = __ffma2_rn(nf, N2(p.fatdt), st.lo);
