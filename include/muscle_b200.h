@@ -207,10 +207,11 @@ int mb_peripheral_fatigue(const MbConfig* cfg, int64_t rows, int64_t L, int32_t 
                           double* fatigue_dev, void* stream);
 
 /* ---- roofline denominators that MEASURED_PEAKS.json does not carry -------------------
- * Dependent-FMA-chain microkernels: each launch executes
- *     blocks * threads * chains * iters   FFMA (kind 0) / DFMA (kind 1) / MUFU.EX2 (kind 2)
- * lane-operations.  The caller times the launch with CUDA events.  `sink_dev` needs
- * blocks*threads elements of 8 bytes. */
+ * Dependent-chain microkernels (8 independent chains per thread): each launch executes
+ *     blocks * threads * 64 * iters
+ * instructions per lane of kind 0 FFMA, 1 DFMA, 2 MUFU.EX2, 3 FFMA2 (packed FP32 pair), 4 FMNMX,
+ * 5 a 5 FFMA : 2 FMNMX : 1 MUFU mix, 6 FMUL2, 7 FADD2.  The caller times the launch with CUDA
+ * events.  `sink_dev` needs blocks*threads elements of 8 bytes. */
 int mb_peak_probe(int32_t kind, int32_t blocks, int32_t threads, int32_t iters,
                   void* sink_dev, int64_t* lane_ops, void* stream);
 

@@ -470,6 +470,35 @@ __global__ void __launch_bounds__(1024) k_peak_probe(int iters, double* sink) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) s += v[i];
         sink[t] = (double)s;
+    } else if (KIND == 6 || KIND == 7) {
+        // packed FP32x2 multiply (6) / add (7): 8 chains of 2 floats
+        unsigned long long v[8], b;
+        {
+            const float bf = (KIND == 6) ? 1.0f - 1e-7f * (float)(t & 7) : 1e-9f * (float)(t & 3);
+            asm("mov.b64 %0, {%1, %1};" : "=l"(b) : "f"(bf));
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float x = 1.0f + 0.01f * (float)i;
+            asm("mov.b64 %0, {%1, %1};" : "=l"(v[i]) : "f"(x));
+        }
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (KIND == 6) asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(v[i]) : "l"(b));
+                    else asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(v[i]) : "l"(b));
+                }
+        }
+        float s = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float lo, hi;
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v[i]));
+            s += lo + hi;
+        }
+        sink[t] = (double)s;
     } else {
         // issue mix of the fused kernel: per 8 "instructions" 5 FFMA, 2 FMNMX, 1 MUFU
         float v[8];
@@ -494,7 +523,7 @@ __global__ void __launch_bounds__(1024) k_peak_probe(int iters, double* sink) {
 
 extern "C" int mb_peak_probe(int32_t kind, int32_t blocks, int32_t threads, int32_t iters, void* sink_dev,
                              int64_t* lane_ops, void* stream) {
-    if (kind < 0 || kind > 5 || blocks <= 0 || threads <= 0 || threads > 1024 || iters <= 0 || !sink_dev)
+    if (kind < 0 || kind > 7 || blocks <= 0 || threads <= 0 || threads > 1024 || iters <= 0 || !sink_dev)
         return fail(MB_EINVAL, "mb_peak_probe: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     if (kind == 0) k_peak_probe<0><<<blocks, threads, 0, st>>>(iters, (double*)sink_dev);
@@ -502,7 +531,9 @@ extern "C" int mb_peak_probe(int32_t kind, int32_t blocks, int32_t threads, int3
     else if (kind == 2) k_peak_probe<2><<<blocks, threads, 0, st>>>(iters, (double*)sink_dev);
     else if (kind == 3) k_peak_probe<3><<<blocks, threads, 0, st>>>(iters, (double*)sink_dev);
     else if (kind == 4) k_peak_probe<4><<<blocks, threads, 0, st>>>(iters, (double*)sink_dev);
-    else k_peak_probe<5><<<blocks, threads, 0, st>>>(iters, (double*)sink_dev);
+    else if (kind == 5) k_peak_probe<5><<<blocks, threads, 0, st>>>(iters, (double*)sink_dev);
+    else if (kind == 6) k_peak_probe<6><<<blocks, threads, 0, st>>>(iters, (double*)sink_dev);
+    else k_peak_probe<7><<<blocks, threads, 0, st>>>(iters, (double*)sink_dev);
     MB_CUDA_OK(cudaGetLastError());
     if (lane_ops) *lane_ops = (int64_t)blocks * threads * 64 * (int64_t)iters;
     return MB_OK;

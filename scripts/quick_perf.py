@@ -29,7 +29,7 @@ def time_cuda(fn, iters=5, warm=2):
 def probes(dev):
     lib = nat.lib()
     sink = torch.empty(148 * 8 * 1024, dtype=torch.float64, device=dev)
-    for kind, name in ((0, "FFMA"), (1, "DFMA"), (2, "MUFU.EX2"), (3, "FFMA2(instr)"), (4, "FMNMX"), (5, "mix5F2A1M")):
+    for kind, name in ((0, "FFMA"), (1, "DFMA"), (2, "MUFU.EX2"), (3, "FFMA2(instr)"), (4, "FMNMX"), (5, "mix5F2A1M"), (6, "FMUL2(instr)"), (7, "FADD2(instr)")):
         ops = C.c_int64()
         iters = 4096 if kind != 1 else 1024
         def run():
