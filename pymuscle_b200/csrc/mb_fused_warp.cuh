@@ -1,4 +1,4 @@
-// mb_fused_warp.cuh -- K2w: the fused K-step kernel for muscles of 33..128 units, FP32 mode.
+// mb_fused_warp.cuh -- K2w: the fused K-step kernel for muscles of 12..128 units, FP32 mode.
 //
 // One WARP owns two consecutive muscles for the whole window and never talks to another
 // warp: lane l holds units l, l+32, l+64, l+96 (UPL = ceil(n/32) of them) of both muscles.

@@ -790,8 +790,9 @@ static int fused_geometry(const MbConfig& c, int64_t M, int32_t n, int32_t K, in
         return MB_OK;
     }
     if (per_row) upt = 1;                                    // block kernels: a thread's instances share one table
-    if (f32 && upt == 0 && n > 32 && n <= 128 && !env_int("MB_FUSED_BLOCK", 0)) {
-        // FP32 mode, 33..128 units: one warp per pair of muscles, no cross-warp reduction
+    if (f32 && upt == 0 && n >= 12 && n <= 128 && !env_int("MB_FUSED_BLOCK", 0)) {
+        // FP32 mode, 12..128 units: one warp per pair of muscles, no cross-warp reduction (below 32 units
+        // lanes idle, but the block kernel's 100+ muscles per block do worse: 3.8e11 at n = 16)
         g->warp_kernel = 1;
         g->U = 2; g->q = kWarpsPerBlock; g->G = 2 * kWarpsPerBlock; g->Gp = g->G; g->T = kWTile;
         g->ns = n; g->npg = 0; g->ptp = 0;
@@ -942,7 +943,9 @@ static int step_fused_impl(const MbConfig* cfg, const void* params_dev, int64_t 
         const int upl = (n + 31) / 32;
 #define MB_W_FORCES(FIB, CEN, UPL_)                                                             \
     (forces ? launch_fused(k2w_f32<FIB, CEN, UPL_, true>, a, g, st) : launch_fused(k2w_f32<FIB, CEN, UPL_, false>, a, g, st))
-#define MB_W_UPL(FIB, CEN) (upl == 4 ? MB_W_FORCES(FIB, CEN, 4) : (upl == 3 ? MB_W_FORCES(FIB, CEN, 3) : MB_W_FORCES(FIB, CEN, 2)))
+#define MB_W_UPL(FIB, CEN)                                                                      \
+    (upl == 4 ? MB_W_FORCES(FIB, CEN, 4)                                                        \
+              : (upl == 3 ? MB_W_FORCES(FIB, CEN, 3) : (upl == 2 ? MB_W_FORCES(FIB, CEN, 2) : MB_W_FORCES(FIB, CEN, 1))))
 #define MB_W_CEN(FIB) (cen == 0 ? MB_W_UPL(FIB, 0) : (cen == 1 ? MB_W_UPL(FIB, 1) : MB_W_UPL(FIB, 2)))
         return fib == MB_FIBERS_POTVIN ? MB_W_CEN(MB_FIBERS_POTVIN) : MB_W_CEN(MB_FIBERS_PYMUSCLE);
 #undef MB_W_CEN
