@@ -126,6 +126,10 @@ int mb_params_pack(const MbConfig* cfg, int64_t L,
  *   totals_dev    [rows, S] per-muscle totals (fibers:276, / output divisor); may be NULL
  *   mask_dev      [rows, L] uint8 recruitment mask (pool:171); may be NULL
  *   rates_dev     [rows, L] adapted firing rates (Pool.step's return); NULL unless wanted
+ * The streaming kernel (stage MUSCLE without mask / rates, device-resident inputs, 16-byte aligned
+ * cpf / dur / per-unit input base pointers) reads the state and per-unit input arrays in whole
+ * 16-byte granules: with an odd rows * L it touches (and ignores) the padding up to the next 16-byte
+ * boundary after the last element, which every CUDA allocator provides.
  */
 int mb_step(const MbConfig* cfg, const void* params_dev,
             int64_t rows, int64_t L, int32_t S, const int32_t* seg_off_dev,
@@ -145,8 +149,8 @@ int mb_step(const MbConfig* cfg, const void* params_dev,
  *   in_dev        [rows, S] one excitation per muscle
  *   out_gain_dev  [rows, S] totals are multiplied by it; may be NULL
  *   fatigue_dev   [rows, S] float64, 1 - sum(new capacities)/output divisor; may be NULL
- * Returns MB_EUNSUPPORTED for layouts the streaming kernel does not cover (odd row length,
- * unaligned state, peripheral fatigue off); the caller then uses mb_step + mb_peripheral_fatigue. */
+ * Returns MB_EUNSUPPORTED for layouts the streaming kernel does not cover (state arrays not
+ * 16-byte aligned, peripheral fatigue off); the caller then uses mb_step + mb_peripheral_fatigue. */
 int mb_step_env(const MbConfig* cfg, const void* params_dev,
                 int64_t rows, int64_t L, int32_t S, const int32_t* seg_off_dev, const double* seg_div_dev,
                 const void* in_dev, double* cpf_dev, double* dur_dev,

@@ -21,11 +21,12 @@
 //                   segment's column tiles and are reduced once per work item (warp
 //                   shuffles + one shared-memory stage, named barrier over the consumers).
 //
-// Bulk copies need 16-byte aligned global addresses: rows are 8-byte elements, so the
-// kernel requires an even row length L and starts each row copy at the even element at or
-// below the tile start (`shift` = 0 or 1, identical for all rows because L is even).
-// Layouts that do not qualify (odd L) and the stage / per-unit-input / mask variants use
-// the generic k1_step kernel instead.
+// Bulk copies need 16-byte aligned global addresses: rows are 8-byte elements, so each row
+// copy starts at the even element at or below the tile start and the consumers skip `shift`
+// = 0 or 1 elements.  With an even row length the shift is the same in all rows; with an odd
+// one it alternates from row to row (a chunk starts at a multiple of 8 rows), which costs the
+// consumers nothing because the row index is a compile-time constant of the unrolled loop.
+// The pool-only / fibers-only stages and the mask / rate outputs use the generic k1_step kernel.
 #pragma once
 
 namespace mb {
@@ -156,27 +157,32 @@ __global__ void __launch_bounds__(288, 2) k1_stream(const K1sArgs<T> a) {
                 mbar_wait(bar0 + 8u * (NS + s), ph ^ 1);  // stage free (passes at once in the first round)
                 const int count = min(W, n - u0);
                 const int64_t e0 = off0 + u0;             // element offset inside a row
-                const int64_t a0 = e0 & ~(int64_t)1, a1 = (e0 + count + 1) & ~(int64_t)1;
-                const uint32_t bytes = (uint32_t)(a1 - a0) * 8u;
                 const uint32_t pbytes = (uint32_t)count * 16u;           // one parameter group of the tile
-                const int64_t i0a = e0 & ~(int64_t)(kInAlign - 1);       // per-unit inputs: 16-byte aligned span of the tile
-                const int64_t i1a = (e0 + count + kInAlign - 1) & ~(int64_t)(kInAlign - 1);
-                const uint32_t ibytes = a.in_per_unit ? (uint32_t)(i1a - i0a) * (uint32_t)sizeof(T) : 0u;
-                const uint32_t ptiles = PERROW ? (uint32_t)nrows : 1u;
-                if (lane == 0)
-                    mbar_expect_tx(bar0 + 8u * s,
-                                   bytes * nrows * (CENTRAL ? 2u : 1u) + pbytes * G * ptiles + ibytes * nrows);
+                // every lane works out what it will copy; the stage's transaction count is the warp's sum
+                const bool state_lane = lane < nrows;
+                const bool input_lane = a.in_per_unit && lane >= 16 && lane < 16 + nrows;   // lanes 16 .. 16+R-1: the input rows
+                const int64_t ge = (r0 + (input_lane ? lane - 16 : lane)) * a.L + e0;       // this lane's row: first element of the tile
+                const int64_t a0 = ge & ~(int64_t)1, a1 = (ge + count + 1) & ~(int64_t)1;   // 16-byte aligned span (8-byte state)
+                const uint32_t bytes = (uint32_t)(a1 - a0) * 8u;
+                const int64_t i0a = ge & ~(int64_t)(kInAlign - 1);                          // ... and of the per-unit inputs
+                const int64_t i1a = (ge + count + kInAlign - 1) & ~(int64_t)(kInAlign - 1);
+                const uint32_t ibytes = (uint32_t)(i1a - i0a) * (uint32_t)sizeof(T);
+                uint32_t mine = state_lane ? bytes * (CENTRAL ? 2u : 1u) : (input_lane ? ibytes : 0u);
+                if (PERROW) {
+                    if (lane == 0) mine += pbytes * G * (uint32_t)nrows;
+                } else if (lane >= R && lane < R + G) {
+                    mine += pbytes;
+                }
+                const uint32_t total = __reduce_add_sync(0xffffffffu, mine);
+                if (lane == 0) mbar_expect_tx(bar0 + 8u * s, total);
                 __syncwarp();
-                if (lane < nrows) {
-                    const int64_t g = (r0 + lane) * a.L + a0;
+                if (state_lane) {
                     const uint32_t so = (uint32_t)((s * R + lane) * rowp) * 8u;
-                    bulk_g2s(smem_u32(cpf_s) + so, a.cpf + g, bytes, bar0 + 8u * s);
-                    if (CENTRAL) bulk_g2s(smem_u32(dur_s) + so, a.dur + g, bytes, bar0 + 8u * s);
+                    bulk_g2s(smem_u32(cpf_s) + so, a.cpf + a0, bytes, bar0 + 8u * s);
+                    if (CENTRAL) bulk_g2s(smem_u32(dur_s) + so, a.dur + a0, bytes, bar0 + 8u * s);
                 }
-                if (a.in_per_unit && lane >= 16 && lane < 16 + nrows) {  // lanes 16 .. 16+R-1: the input rows
-                    const int r = lane - 16;
-                    bulk_g2s(smem_u32(in_s + (size_t)(s * R + r) * rowpi), a.in + (r0 + r) * a.L + i0a, ibytes, bar0 + 8u * s);
-                }
+                if (input_lane)
+                    bulk_g2s(smem_u32(in_s + (size_t)(s * R + lane - 16) * rowpi), a.in + i0a, ibytes, bar0 + 8u * s);
                 if (!PERROW) {
                     if (lane >= R && lane < R + G) {
                         const int grp = lane - R;                        // lanes R .. R+G-1: the parameter groups
@@ -229,25 +235,29 @@ __global__ void __launch_bounds__(288, 2) k1_stream(const K1sArgs<T> a) {
             const uint32_t s = it % NS, ph = (it / NS) & 1;
             const int u = u0 + tid;
             const bool active = u < n;
-            const int shift = (off0 + u0) & 1;
+            // first wanted element of a staged row: r0 * L is even (r0 is a multiple of 8), so row r starts
+            // at parity (r * L + off0 + u0) & 1 -- the same in all rows for even L, alternating for odd L
+            const int sh0 = (off0 + u0) & 1, sh1 = sh0 ^ (int)(a.L & 1);
             mbar_wait(bar0 + 8u * s, ph);
             if (active) {
                 const P* pst = par_s + (size_t)(s * PR * G) * W;
                 auto p = load_unit_staged(pst, W, tid);
                 double fatdt = (double)p.fat * a.dt, rdidt = (double)p.rdi * a.dt;
                 double ptf = unit_peak(p);
-                const double* cs = cpf_s + (s * R) * rowp + shift + tid;
-                const double* ds = dur_s + (s * R) * rowp + shift + tid;
+                const double* cs = cpf_s + (s * R) * rowp + tid;
+                const double* ds = dur_s + (s * R) * rowp + tid;
                 double c[R], d[R];
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    c[r] = cs[r * rowp];
-                    d[r] = CENTRAL ? ds[r * rowp] : 0.0;
+                    const int sh = (r & 1) ? sh1 : sh0;
+                    c[r] = cs[r * rowp + sh];
+                    d[r] = CENTRAL ? ds[r * rowp + sh] : 0.0;
                 }
                 if (a.in_per_unit) {                                 // this unit's own excitation in every row
-                    const T* xs = in_s + (size_t)(s * R) * rowpi + ((off0 + u0) & (kInAlign - 1)) + tid;
+                    const T* xs = in_s + (size_t)(s * R) * rowpi + tid;
+                    const int em = (off0 + u0) & (kInAlign - 1), lm = (int)(a.L & (kInAlign - 1));
 #pragma unroll
-                    for (int r = 0; r < R; ++r) xm[r] = xs[r * rowpi];
+                    for (int r = 0; r < R; ++r) xm[r] = xs[r * rowpi + ((r * lm + em) & (kInAlign - 1))];
                 }
                 const int64_t i0 = r0 * a.L + off0 + u;
                 T* fp = FORCES ? a.forces + i0 : nullptr;

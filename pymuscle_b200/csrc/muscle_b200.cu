@@ -547,12 +547,19 @@ static int env_int(const char* name, int dflt) {
     return (v && *v) ? atoi(v) : dflt;
 }
 
+static int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return dev;
+}
+
 static int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    // cached per device: one process may drive several GPUs
+    static thread_local int c_dev = -1, n = 0;
+    const int dev = current_device();
+    if (dev != c_dev) {
         if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        c_dev = dev;
     }
     return n;
 }
@@ -599,13 +606,15 @@ static int launch_k1s_variant(const K1sArgs<T>& a, int threads, int smem, int64_
     // persistent grid: exactly the blocks that are resident at once, each walking the work list.
     // The opt-in and the occupancy query are cached per (instantiation, geometry): a batch-of-1 drop-in
     // step is only ~20 us long, so two driver calls per launch would show.
-    static thread_local int c_threads = -1, c_smem = -1, c_per_sm = 0;
-    if (c_threads != threads || c_smem != smem) {
+    // The function attribute is per device, so the device is part of the key.
+    static thread_local int c_dev = -1, c_threads = -1, c_smem = -1, c_per_sm = 0;
+    const int dev = current_device();
+    if (c_dev != dev || c_threads != threads || c_smem != smem) {
         if (smem > 48 * 1024) MB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int q = 0;
         MB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, threads, smem));
         if (q < 1) return fail(MB_ECUDA, "k1_stream does not fit on an SM (threads %d, smem %d)", threads, smem);
-        c_threads = threads; c_smem = smem; c_per_sm = q;
+        c_dev = dev; c_threads = threads; c_smem = smem; c_per_sm = q;
     }
     int per_sm = c_per_sm;
     const int cap = env_int("MB_K1_BPS", 0);
@@ -617,8 +626,8 @@ static int launch_k1s_variant(const K1sArgs<T>& a, int threads, int smem, int64_
     return MB_OK;
 }
 
-// The streaming kernel covers the batched hot case: whole-muscle stage, one input per muscle,
-// no mask / rate outputs, even row length, 16-byte aligned state arrays.
+// The streaming kernel covers the batched hot case: whole-muscle stage, one input per muscle or per unit,
+// no mask / rate outputs, 16-byte aligned state arrays (any row length).
 template <typename T>
 static bool k1s_eligible(const MbConfig& c, int64_t L, int32_t stage, int32_t in_per_unit, const void* in,
                          const double* cpf, const double* dur, const uint8_t* mask, const void* rates,
@@ -627,16 +636,17 @@ static bool k1s_eligible(const MbConfig& c, int64_t L, int32_t stage, int32_t in
     // per-instance tables: FP32 mode with the force output and without the fatigue epilogue (one instantiation set)
     if (c.param_rows > 1 && (sizeof(T) != 4 || !forces || fatigue)) return false;
     if (stage != MB_STAGE_MUSCLE || mask || rates || !c.peripheral_fatigue) return false;
-    // per-unit inputs are staged with bulk copies too: rows must start on 16-byte boundaries
+    // per-unit inputs are staged with bulk copies too (any row length: the copies start at the 16-byte
+    // boundary at or below each row's tile start)
     if (in_per_unit) {
-        if (L % (16 / (int)sizeof(T)) != 0 || ((uintptr_t)in % 16) != 0) return false;
+        if (((uintptr_t)in % 16) != 0) return false;
         cudaPointerAttributes at;                             // (the drop-in classes pass pinned HOST memory)
         if (cudaPointerGetAttributes(&at, in) != cudaSuccess || at.type != cudaMemoryTypeDevice) {
             cudaGetLastError();
             return false;
         }
     }
-    if (L % 2 != 0 || ((uintptr_t)cpf % 16) != 0) return false;
+    if (((uintptr_t)cpf % 16) != 0) return false;
     if (c.central_fatigue && ((uintptr_t)dur % 16) != 0) return false;
     return true;
 }
@@ -734,12 +744,12 @@ extern "C" int mb_step_env(const MbConfig* cfg, const void* params_dev, int64_t 
     cudaStream_t st = (cudaStream_t)stream;
     if (cfg->precision == MB_F32) {
         if (!k1s_eligible<float>(*cfg, L, MB_STAGE_MUSCLE, 0, in_dev, cpf_dev, dur_dev, nullptr, nullptr, forces_dev, fatigue_dev))
-            return fail(MB_EUNSUPPORTED, "mb_step_env needs an even row length, 16-byte aligned state and peripheral fatigue on");
+            return fail(MB_EUNSUPPORTED, "mb_step_env needs 16-byte aligned state arrays and peripheral fatigue on");
         return launch_k1s<float>(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, in_dev, 0, cpf_dev, dur_dev,
                                  forces_dev, totals_dev, out_gain_dev, fatigue_dev, step_size, st, scal_f(*cfg));
     }
     if (!k1s_eligible<double>(*cfg, L, MB_STAGE_MUSCLE, 0, in_dev, cpf_dev, dur_dev, nullptr, nullptr, forces_dev, fatigue_dev))
-        return fail(MB_EUNSUPPORTED, "mb_step_env needs an even row length, 16-byte aligned state and peripheral fatigue on");
+        return fail(MB_EUNSUPPORTED, "mb_step_env needs 16-byte aligned state arrays and peripheral fatigue on");
     return launch_k1s<double>(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, in_dev, 0, cpf_dev, dur_dev,
                               forces_dev, totals_dev, out_gain_dev, fatigue_dev, step_size, st, scal_d(*cfg));
 }

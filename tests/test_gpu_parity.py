@@ -383,3 +383,66 @@ def test_host_pipeline_matches_the_device_path(cuda_device, overlap):
     c = MuscleBatch(MuscleSpec.potvin(n), M, cuda_device, "f32", fresh_outputs=False)
     whole = c.step_many(excs[0].to(cuda_device), dt)
     close(out_h[0].numpy(), whole.double().cpu().numpy(), "f32", 2609.03, "sub-windows vs one window")
+
+
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+@pytest.mark.parametrize("kind,n", [("potvin", 121), ("potvin", 57), ("standard", 299), ("standard", 1999)])
+def test_odd_row_lengths_in_the_streaming_kernel(cuda_device, kind, n, precision):
+    """Odd unit counts: consecutive float64 state rows alternate between 16-byte aligned and not, so the
+    streaming kernel's bulk copies start one element early in every other row.  Odd number of rows too
+    (partial last chunk, odd element count overall), per-muscle and per-unit inputs, fatigue epilogue."""
+    from pymuscle_b200.tables import fibers_tables
+    rng = np.random.default_rng(n)
+    rows, K = 11, 25
+    if kind == "potvin":
+        spec, scale = MuscleSpec.potvin(n), 67.0
+    else:
+        base = MuscleSpec.standard()
+        spec, scale = MuscleSpec(n, base.pool, base.fibers, input_scale=base.input_scale,
+                                 output_divisor=sum(fibers_tables(n, base.fibers)[0]), name="standard"), 1.0
+    ora, ora_u = OracleMuscles(n, rows, kind), OracleMuscles(n, rows, kind)
+    ptf = spec.tables()["ptf"]
+    tscale = float(np.sum(ptf)) / spec.output_divisor
+    b, bu = MuscleBatch(spec, rows, cuda_device, precision), MuscleBatch(spec, rows, cuda_device, precision)
+    for k in range(K):
+        e = (scale * rng.random(rows)).astype(np.float32)
+        eu = (scale * rng.random((rows, n))).astype(np.float32)
+        want, want_u = ora.step(e.astype(np.float64), 0.05), ora_u.step(eu.astype(np.float64), 0.05)
+        if k % 2:
+            got, fat = b.step_env(torch.from_numpy(e).to(cuda_device, b.dtype), 0.05)       # fused fatigue epilogue
+            if kind == "standard":
+                close(fat.cpu().numpy(), ora.peripheral_fatigue(), precision, 1.0, f"fatigue step {k}")
+        else:
+            got = b.step(torch.from_numpy(e).to(cuda_device, b.dtype), 0.05)
+        got_u = bu.step(torch.from_numpy(eu).to(cuda_device, b.dtype), 0.05)
+        close(got.cpu().numpy(), want.total, precision, tscale, f"totals step {k}")
+        close(got_u.cpu().numpy(), want_u.total, precision, tscale, f"per-unit-input totals step {k}")
+        close(b.current_forces.cpu().numpy(), want.forces, precision, ptf, f"forces step {k}")
+        close(bu.current_forces.cpu().numpy(), want_u.forces, precision, ptf, f"per-unit-input forces step {k}")
+    close(b.cpf.cpu().numpy(), ora.cpf, precision, ptf, "capacities")
+    close(bu.cpf.cpu().numpy(), ora_u.cpf, precision, ptf, "per-unit-input capacities")
+    np.testing.assert_allclose(b.dur.cpu().numpy(), ora.dur, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(bu.dur.cpu().numpy(), ora_u.dur, rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_ragged_rows_with_an_odd_row_length(cuda_device, precision):
+    """Three StandardMuscles of 256 + 280 + 305 = 841 units per row: odd row length AND odd segment
+    offsets, five rows (partial chunk); totals, forces, capacities and the fused fatigue epilogue."""
+    forces = [round(68.0 * (824.0 / 68.0) ** (i / 29.0), 1) for i in range(3)]
+    specs = [MuscleSpec.standard(f) for f in forces]
+    assert sum(s.n for s in specs) == 841
+    rows, rng = 5, np.random.default_rng(3)
+    oras = [OracleMuscles.standard(f, m=rows) for f in forces]
+    b = MuscleBatch(specs, rows, cuda_device, precision)
+    offs = np.cumsum([0] + [s.n for s in specs])
+    for k in range(20):
+        e = rng.random((rows, 3)).astype(np.float32)
+        got, fat = b.step_env(torch.from_numpy(e).to(cuda_device, b.dtype), 0.1)
+        for j, (o, s) in enumerate(zip(oras, specs)):
+            want = o.step(e[:, j].astype(np.float64), 0.1)
+            ptf = s.tables()["ptf"]
+            close(got[:, j].cpu().numpy(), want.total, precision, 1.0, f"totals muscle {j} step {k}")
+            close(b.current_forces[:, offs[j]:offs[j + 1]].cpu().numpy(), want.forces, precision, ptf, f"forces {j}/{k}")
+            close(b.cpf[:, offs[j]:offs[j + 1]].cpu().numpy(), o.cpf, precision, ptf, f"capacities {j}/{k}")
+            close(fat[:, j].cpu().numpy(), o.peripheral_fatigue(), precision, 1.0, f"fatigue {j}/{k}")
