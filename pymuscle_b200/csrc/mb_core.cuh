@@ -233,6 +233,30 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// Eight independent warp sums at once ("transposing" butterfly): every exchange halves the number of
+// values a lane carries, so 4 + 2 + 1 + 2 = 9 shuffles replace the 40 of eight separate warp_sum calls.
+// Afterwards every lane holds the warp total of row (lane >> 2) & 7.  Fixed order => deterministic.
+template <typename T>
+__device__ __forceinline__ T warp_sum_rows8(const T (&v)[8], int lane) {
+    const bool up16 = lane & 16, up8 = lane & 8, up4 = lane & 4;
+    T a[4], b[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {                                      // lanes with bit 4 keep rows 4..7
+        const T keep = up16 ? v[i + 4] : v[i], send = up16 ? v[i] : v[i + 4];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {                                      // bit 3 picks rows +2, +3
+        const T keep = up8 ? a[i + 2] : a[i], send = up8 ? a[i] : a[i + 2];
+        b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    const T keep = up4 ? b[1] : b[0], send = up4 ? b[0] : b[1];        // bit 2 picks row +1
+    T r = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    r += __shfl_xor_sync(0xffffffffu, r, 2);
+    r += __shfl_xor_sync(0xffffffffu, r, 1);
+    return r;
+}
+
 // the float64 peak twitch force, exactly (a rested unit has capacity == peak, and must keep it)
 __device__ __forceinline__ double unit_peak(const UnitF& p) { return ((double)p.ptf + (double)p.ptf_lo) + (double)p.ptf_lo2; }
 __device__ __forceinline__ double unit_peak(const UnitD& p) { return p.ptf; }

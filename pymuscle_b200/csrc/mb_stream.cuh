@@ -34,8 +34,23 @@ namespace mb {
 constexpr int kStreamRows = 8;          // R: rows advanced together by a block
 
 template <typename T> struct StreamTraits;
-template <> struct StreamTraits<float>  { using U = UnitF; using P = float4;  using S = ScalF; static constexpr int G = kGroupsF32; };
-template <> struct StreamTraits<double> { using U = UnitD; using P = double2; using S = ScalD; static constexpr int G = kGroupsF64; };
+// kMaxW / kMaxWCentral: widest column tile (= consumer threads per block) without / with central fatigue;
+// kMinBlocks / kMinBlocksCentral: resident blocks the register budget is sized for; kDefStages: ring depth.
+// FP64 mode carries twice the registers per row value: with the FP32 geometry (288 threads x 2 blocks = 96
+// registers) its consumers spilled up to 300 bytes per thread, so it runs narrower blocks with more registers
+// (128 without central fatigue -- no spills; 168 with it) and a deeper ring to keep the bytes in flight.
+#ifndef MB_K1F_CENTRAL_MAXW
+#define MB_K1F_CENTRAL_MAXW 256
+#define MB_K1F_CENTRAL_MINB 2
+#endif
+template <> struct StreamTraits<float>  { using U = UnitF; using P = float4;  using S = ScalF; static constexpr int G = kGroupsF32;
+                                          static constexpr int kMaxW = 256, kMinBlocks = 2;
+                                          static constexpr int kMaxWCentral = MB_K1F_CENTRAL_MAXW, kMinBlocksCentral = MB_K1F_CENTRAL_MINB;
+                                          static constexpr int kDefStages = 2; };
+template <> struct StreamTraits<double> { using U = UnitD; using P = double2; using S = ScalD; static constexpr int G = kGroupsF64;
+                                          static constexpr int kMaxW = 128, kMinBlocks = 3;
+                                          static constexpr int kMaxWCentral = 64, kMinBlocksCentral = 4;
+                                          static constexpr int kDefStages = 3; };
 
 template <typename T>
 struct K1sArgs {
@@ -81,21 +96,28 @@ template <bool CENTRAL, bool RECOVERY>
 __device__ __forceinline__ double k1s_unit(const K1sArgs<double>& a, const UnitD& p, double x, double c, double d,
                                            double fatdt, double rdidt, double ptf, double& cn, double& dn,
                                            const double* exp_tab) {
+    // both exponentials (adaptation exp(-dur/tau), pool:213-221; force sigmoid, fibers:247-252) go through the
+    // table-based exp_neg_fast (relative error < 1e-14 against the mode's 1e-9 bar): the library exp costs
+    // ~2.5x the FP64 instructions and this kernel is FP64-pipe bound, not HBM bound
     bool on;
     const double r = pool_rate(p, a.sc, x, on);
     double fr = r;
     if (CENTRAL) {
-        fr = pool_adapt(p, a.sc, r, d);
+        const double q = fma(r, p.phir, -p.phir6);
+        const double ad = q * (1.0 - exp_neg_fast<true>(d * a.sc.mitau, exp_tab));
+        fr = r - ((ad < 0.0) ? 0.0 : ad);                               // pool:205-206, :121
         dn = duration_update(d, r > 0.0, a.dt, a.max_dur);
     }
     double nf;
-    const double F = fibers_force(p, a.sc, fr, c, nf);
+    const double F = fibers_force_fast<true>(p, a.sc, fr, c, nf, exp_tab);
     cn = fatigue_update<RECOVERY>(c, nf, fatdt, rdidt, ptf);
     return F;
 }
 
 template <typename T, bool CENTRAL, bool RECOVERY, bool FORCES, bool FATIGUE, bool PERROW = false>
-__global__ void __launch_bounds__(288, 2) k1_stream(const K1sArgs<T> a) {
+__global__ void __launch_bounds__((CENTRAL ? StreamTraits<T>::kMaxWCentral : StreamTraits<T>::kMaxW) + 32,
+                  CENTRAL ? StreamTraits<T>::kMinBlocksCentral : StreamTraits<T>::kMinBlocks)
+k1_stream(const K1sArgs<T> a) {
     constexpr int R = kStreamRows;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int W = a.W, NS = a.NS;
@@ -141,13 +163,15 @@ __global__ void __launch_bounds__(288, 2) k1_stream(const K1sArgs<T> a) {
 
     const int64_t chunks = (a.rows + R - 1) / R;
     const int64_t items = chunks * a.S;
+    // work item -> (chunk, segment) without a division per item: a block's items are gridDim.x apart
+    const int step_chunks = (int)(gridDim.x / (unsigned)a.S), step_segs = (int)(gridDim.x % (unsigned)a.S);
 
     if (warp == ncw) {
         // ------------------------------ producer warp ----------------------------------------
         uint32_t it = 0;
+        int64_t chunk = (int64_t)(blockIdx.x / (unsigned)a.S);
+        int seg = (int)(blockIdx.x % (unsigned)a.S);
         for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
-            const int64_t chunk = item / a.S;
-            const int seg = (int)(item - chunk * a.S);
             const int64_t r0 = chunk * R;
             const int off0 = seg_off ? seg_off[seg] : 0;
             const int n = seg_off ? seg_off[seg + 1] - off0 : (int)a.L;
@@ -198,26 +222,32 @@ __global__ void __launch_bounds__(288, 2) k1_stream(const K1sArgs<T> a) {
                     }
                 }
             }
+            chunk += step_chunks;
+            seg += step_segs;
+            if (seg >= a.S) { seg -= a.S; ++chunk; }
         }
         return;
     }
 
     // ---------------------------------- consumer warps ----------------------------------------
     // the per-muscle inputs of the NEXT work item are fetched while the current one is processed
-    auto fetch_inputs = [&](int64_t item, T (&x)[R]) {
-        const int64_t chunk = item / a.S;
-        const int seg = (int)(item - chunk * a.S);
+    auto fetch_inputs = [&](int64_t chunk, int seg, T (&x)[R]) {
         const int64_t r0 = chunk * R;
 #pragma unroll
         for (int r = 0; r < R; ++r)
-            x[r] = (!a.in_per_unit && item < items && r0 + r < a.rows) ? a.in[(r0 + r) * a.S + seg] : T(0);
+            x[r] = (!a.in_per_unit && r0 + r < a.rows) ? a.in[(r0 + r) * a.S + seg] : T(0);
     };
     uint32_t it = 0, item_no = 0;
     T xnext[R];
-    fetch_inputs(blockIdx.x, xnext);
+    int64_t chunk_next = (int64_t)(blockIdx.x / (unsigned)a.S);
+    int seg_next = (int)(blockIdx.x % (unsigned)a.S);
+    fetch_inputs(chunk_next, seg_next, xnext);
     for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
-        const int64_t chunk = item / a.S;
-        const int seg = (int)(item - chunk * a.S);
+        const int64_t chunk = chunk_next;
+        const int seg = seg_next;
+        chunk_next += step_chunks;
+        seg_next += step_segs;
+        if (seg_next >= a.S) { seg_next -= a.S; ++chunk_next; }
         const int64_t r0 = chunk * R;
         const int off0 = seg_off ? seg_off[seg] : 0;
         const int n = seg_off ? seg_off[seg + 1] - off0 : (int)a.L;
@@ -230,7 +260,7 @@ __global__ void __launch_bounds__(288, 2) k1_stream(const K1sArgs<T> a) {
             xm[r] = xnext[r];
         }
         constexpr bool want_fatigue = FATIGUE;                // fused get_peripheral_fatigue epilogue
-        fetch_inputs(item + gridDim.x, xnext);
+        fetch_inputs(chunk_next, seg_next, xnext);                // (rows past the end read as 0)
         for (int u0 = 0; u0 < n; u0 += W, ++it) {
             const uint32_t s = it % NS, ph = (it / NS) & 1;
             const int u = u0 + tid;
@@ -297,17 +327,13 @@ __global__ void __launch_bounds__(288, 2) k1_stream(const K1sArgs<T> a) {
             // scratch alternates between consecutive items, so ONE barrier per item is enough: a warp
             // reaches the next write of the same half only after the barrier of the item in between
             T* red = red0 + (item_no++ & 1) * (2 * R * 8);
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const T w = warp_sum(partial[r]);
-                if (lane == 0) red[r * 8 + warp] = w;
-            }
+            static_assert(R == 8, "warp_sum_rows8 reduces exactly eight rows");
+            const int rr = (lane >> 2) & 7;                       // the row whose warp total this lane ends up with
+            const T wf = warp_sum_rows8(partial, lane);
+            if ((lane & 3) == 0) red[rr * 8 + warp] = wf;
             if (want_fatigue) {
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const T w = warp_sum(csum[r]);
-                    if (lane == 0) red[(R + r) * 8 + warp] = w;
-                }
+                const T wc = warp_sum_rows8(csum, lane);
+                if ((lane & 3) == 0) red[(R + rr) * 8 + warp] = wc;
             }
             asm volatile("bar.sync 1, %0;" ::"r"(ncons) : "memory");
             if (tid < nrows) {

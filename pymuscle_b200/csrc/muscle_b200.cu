@@ -671,14 +671,17 @@ static int launch_k1s(const MbConfig& c, const void* params, int64_t rows, int64
     const int64_t mean_n = (L + S - 1) / S;
     int W = (int)((mean_n + 31) / 32) * 32;
     // per-instance tables put R parameter tiles into every stage: narrower tiles keep two stages within reach
-    const int wmax = env_int("MB_K1_W", c.param_rows > 1 ? 64 : 256);
+    const int wcap = central ? StreamTraits<T>::kMaxWCentral : StreamTraits<T>::kMaxW;   // the instantiation's launch bound
+    int wmax = env_int("MB_K1_W", c.param_rows > 1 ? 64 : wcap);
+    if (wmax > wcap) wmax = wcap;
     if (W > wmax) W = wmax;
     if (W < 32) W = 32;
     const int stage_bytes = kStreamRows * (W + 2) * 8 * (central ? 2 : 1) +                                // state rows
                             StreamTraits<T>::G * W * 16 * (c.param_rows > 1 ? kStreamRows : 1) +         // + unit parameters
                             (in_per_unit ? kStreamRows * (W + 2 * (16 / (int)sizeof(T))) * (int)sizeof(T) : 0);   // + per-unit inputs
     int NS = env_int("MB_K1_STAGES", 0);
-    if (NS <= 0) NS = 2;                                      // measured: double buffering x 2+ blocks/SM saturates HBM; deeper rings only cost occupancy
+    if (NS <= 0) NS = StreamTraits<T>::kDefStages;            // measured: FP32 mode: double buffering x 2 blocks/SM saturates HBM, deeper rings
+                                                              // only cost occupancy; FP64 mode (3-4 narrower blocks per SM): three stages
     if (NS > 8) NS = 8;
     if (NS < 2) NS = 2;
     a.W = W; a.NS = NS;
