@@ -446,3 +446,29 @@ def test_ragged_rows_with_an_odd_row_length(cuda_device, precision):
             close(b.current_forces[:, offs[j]:offs[j + 1]].cpu().numpy(), want.forces, precision, ptf, f"forces {j}/{k}")
             close(b.cpf[:, offs[j]:offs[j + 1]].cpu().numpy(), o.cpf, precision, ptf, f"capacities {j}/{k}")
             close(fat[:, j].cpu().numpy(), o.peripheral_fatigue(), precision, 1.0, f"fatigue {j}/{k}")
+
+
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+@pytest.mark.parametrize("kind", ["potvin", "standard"])
+def test_generic_single_step_kernel_agrees_with_the_streaming_kernel(cuda_device, kind, precision, monkeypatch):
+    """The generic k1_step kernel is what mask / rate outputs, stage launches and host-resident inputs use;
+    for the whole-muscle stage it must give what the streaming kernel gives (MB_K1_GENERIC=1 forces it).
+    State and forces are per-unit results of the same arithmetic: bitwise equal; totals differ only by the
+    order of the per-muscle sum."""
+    rng = np.random.default_rng(17)
+    rows, n, K = 19, 120, 12
+    spec = MuscleSpec.potvin(n) if kind == "potvin" else MuscleSpec.standard()
+    scale = 67.0 if kind == "potvin" else 1.0
+    a, b = MuscleBatch(spec, rows, cuda_device, precision), MuscleBatch(spec, rows, cuda_device, precision)
+    for k in range(K):
+        x = torch.from_numpy((scale * rng.random(rows)).astype(np.float32)).to(cuda_device, a.dtype)
+        ta = a.step(x, 0.05)
+        monkeypatch.setenv("MB_K1_GENERIC", "1")
+        tb = b.step(x, 0.05)
+        monkeypatch.delenv("MB_K1_GENERIC")
+        if precision == "f32":      # FP64 mode: the streaming kernel uses the table-based exp, the generic one the library's
+            assert torch.equal(a.cpf, b.cpf) and torch.equal(a.dur, b.dur)
+            assert torch.equal(a.current_forces, b.current_forces)
+        close(tb.cpu().numpy(), ta.double().cpu().numpy(), precision, total_scale(spec), f"totals step {k}")
+    close(b.cpf.cpu().numpy(), a.cpf.cpu().numpy(), precision, spec.tables()["ptf"], "capacities")
+    close(b.current_forces.cpu().numpy(), a.current_forces.double().cpu().numpy(), precision, spec.tables()["ptf"], "forces")
