@@ -205,13 +205,21 @@ __device__ __forceinline__ double fibers_force(const UnitD& p, const ScalD& s, d
 // fatdt = fat*dt, rdidt = (rec/ptf)*dt (both zero when peripheral fatigue is off).  The
 // recovery term is written (ptf - c) * rdidt so that it is exactly 0 for a rested unit,
 // as in the reference's rec * ((ptf - c)/ptf) * dt.
+// c < 0 ? 0 : c on the bit pattern: three integer instructions and no predicate instead of an FP64
+// compare and two selects (-0.0 becomes +0.0, which compares equal)
+__device__ __forceinline__ double zero_if_negative(double c) {
+    const int hi = __double2hiint(c);
+    const int keep = ~(hi >> 31);
+    return __hiloint2double(hi & keep, __double2loint(c) & keep);
+}
+
 template <bool RECOVERY>
 __device__ __forceinline__ double fatigue_update(double cpf, double nf, double fatdt, double rdidt, double ptf) {
     double c = fma(-nf, fatdt, cpf);                                    // fibers:110-111
     if (RECOVERY) {
         if (nf <= 0.0) c = fma(ptf - c, rdidt, c);                      // pmf:121-141
     }
-    c = (c < 0.0) ? 0.0 : c;                                            // fibers:114
+    c = zero_if_negative(c);                                            // fibers:114
     if (RECOVERY) c = (c > ptf) ? ptf : c;                              // pmf:104-105
     return c;
 }

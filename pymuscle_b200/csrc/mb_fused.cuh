@@ -377,10 +377,11 @@ struct CoreF32 {
 };
 
 // ---- FP64 mode ------------------------------------------------------------------------
-// Durations are accumulated exactly as the reference does (dur += dt, clamped).  The
-// adaptation factor E = exp(-dur/tau) is carried by recurrence (a firing step multiplies it
-// by exp(-dt/tau); a clamped duration pins it to exp(-max_duration/tau)) and recomputed
-// with a full-precision exp at every tile start, so its error stays at a few ulps.
+// The adaptation factor E = exp(-dur/tau) is carried by recurrence: a firing step multiplies it
+// by exp(-dt/tau).  General path (CENTRAL == 2): durations are accumulated exactly as the
+// reference does (dur += dt, clamped), a clamped duration pins E to exp(-max_duration/tau), and E
+// is recomputed with a full-precision exp at every tile start.  Fast path (CENTRAL == 1): see
+// begin_tile().
 template <int FIB, int CENTRAL, int U>
 struct CoreF64 {
     using T = double;
@@ -390,6 +391,7 @@ struct CoreF64 {
     ScalD sc;
     double fatdt, rdidt, dt, max_dur, decay, Emax;
     double cpf[U], dur[U], E[U];
+    int cnt[U];                  // CENTRAL == 1: on-steps since the window started (dur[] stays at its start value)
     const double* tab;           // shared-memory copy of kExp2Tab
 
     __device__ __forceinline__ void load(const K2Args& a, int u, int64_t muscle) {
@@ -408,10 +410,16 @@ struct CoreF64 {
     __device__ __forceinline__ void init(int j, const K2Args&, double c, double d0) {
         cpf[j] = c;
         dur[j] = d0;
-        E[j] = 1.0;
+        cnt[j] = 0;
+        E[j] = CENTRAL ? exp(d0 * sc.mitau) : 1.0;                         // pool:217-218
     }
+    // Fast path: E = exp(-dur/tau) is carried by the recurrence alone for the whole window -- every on-step
+    // multiplies it by exp(-dt/tau), half an ulp of relative error each, i.e. ~1e-13 after 1,000 steps against the
+    // mode's 1e-9 bar -- and the duration is the start value plus an integer count of on-steps (the reference's
+    // min(dur + dt, max) per on-step, pool:196-203, is monotone, so the clamp can wait until the state is stored).
+    // General path: resynchronised with a full-precision exp at every tile start.
     __device__ __forceinline__ void begin_tile() {
-        if (CENTRAL) {
+        if (CENTRAL == 2) {
 #pragma unroll
             for (int j = 0; j < U; ++j) E[j] = exp(dur[j] * sc.mitau);     // pool:217-218
         }
@@ -421,15 +429,23 @@ struct CoreF64 {
     // are positive (so "rate > 0" is the recruitment mask), that the duration clamp cannot change
     // exp(-dur/tau) in float64, and that the sigmoid's exponent stays above -700
     __device__ __forceinline__ double step(int j, double e, bool& on) {
-        const double r = pool_rate(p, sc, e, on);
-        double fr = r;
+        double r, fr;
         if (CENTRAL == 1) {
+            // pool_rate() without zeroing the rate of an unrecruited unit: the select below does it
+            const double r0 = __dadd_rn(__dsub_rn(__dmul_rn(e, sc.input_scale), p.thr), sc.min_rate);   // muscle.py:275, pool:169-170
+            on = !(r0 < sc.min_rate);                                      // pool:171
+            r = fmin(r0 * sc.gain, p.peak);                                // pool:173, :176-177
             const double q = fma(r, p.phir, -p.phir6);                     // pool:231-232
             fr = on ? fma(-q, 1.0 - E[j], r) : 0.0;                        // pool:217-221, :121 (dur BEFORE the update)
-            const double dn = fmin(dur[j] + dt, max_dur);                  // pool:196-203
-            dur[j] = on ? dn : dur[j];
-            E[j] = on ? E[j] * decay : E[j];
-        } else if (CENTRAL == 2) {
+            if (on) {
+                cnt[j] += 1;
+                E[j] *= decay;
+            }
+        } else {
+            r = pool_rate(p, sc, e, on);
+            fr = r;
+        }
+        if (CENTRAL == 2) {
             const double q = fma(r, p.phir, -p.phir6);                     // pool:231-232
             const double ad = q * (1.0 - E[j]);                            // pool:217-219 (dur BEFORE the update)
             fr = r - ((ad < 0.0) ? 0.0 : ad);                              // pool:221, :121
@@ -458,7 +474,8 @@ struct CoreF64 {
     __device__ __forceinline__ void set_table(const double* t) { tab = t; }
     __device__ __forceinline__ void store(int j, const K2Args& a, int64_t idx) {
         if (a.peripheral) a.cpf[idx] = cpf[j];
-        if (CENTRAL) a.dur[idx] = dur[j];
+        if (CENTRAL == 1) a.dur[idx] = fmin(fma((double)cnt[j], dt, dur[j]), max_dur);       // pool:196-203
+        if (CENTRAL == 2) a.dur[idx] = dur[j];
     }
     __device__ __forceinline__ double out_scale(double v) const { return v / sc.out_div; }   // muscle.py:278
 };
