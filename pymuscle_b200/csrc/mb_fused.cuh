@@ -428,7 +428,7 @@ struct CoreF64 {
     // checked that the adaptation of a recruited unit cannot be negative, that gain and minimal rate
     // are positive (so "rate > 0" is the recruitment mask), that the duration clamp cannot change
     // exp(-dur/tau) in float64, and that the sigmoid's exponent stays above -700
-    __device__ __forceinline__ double step(int j, double e, bool& on) {
+    __device__ __forceinline__ double rate(int j, double e, bool& on) {
         double r, fr;
         if (CENTRAL == 1) {
             // pool_rate() without zeroing the rate of an unrecruited unit: the select below does it
@@ -456,18 +456,38 @@ struct CoreF64 {
                 E[j] = clamp ? Emax : E[j] * decay;
             }
         }
-        double nf;
-        const double F = fibers_force_fast<CENTRAL != 1>(p, sc, fr, cpf[j], nf, tab);
-        cpf[j] = fatigue_update<FIB == MB_FIBERS_PYMUSCLE>(cpf[j], nf, fatdt, rdidt, p.ptf);
-        return F;
+        return fr;
     }
+    // The U instances of a thread advance in three phases so that their FP64 chains interleave: a branch
+    // per instance around the sigmoid's exponential (as in fibers_force_fast) would serialise them -- the
+    // scheduler cannot move instructions across the branches, and ncu showed 40 % of the stall samples on
+    // fixed-latency dependencies of the lone Horner chain.  Here one branch decides for all U instances, and
+    // inside it the U exponentials are straight-line code.
     __device__ __forceinline__ void step_vec(const V& e, V& f, unsigned& onbits) {
         onbits = 0;
+        double x[U];
+        bool need = false;
 #pragma unroll
         for (int j = 0; j < U; ++j) {
             bool on;
-            f.v[j] = step(j, e.v[j], on);
+            const double fr = rate(j, e.v[j], on);
             onbits |= (on ? 1u : 0u) << j;
+            x[j] = fma(cpf[j], -p.ctB, p.ctA) * fr;                        // fibers:220 with the fatigued contraction time
+            need |= x[j] > kLinThrD;
+        }
+        double ex[U];
+        if (need) {
+#pragma unroll
+            for (int j = 0; j < U; ++j) ex[j] = exp_neg_fast<CENTRAL != 1>(-2.0 * (x[j] * x[j] * x[j]), tab);
+        } else {
+#pragma unroll
+            for (int j = 0; j < U; ++j) ex[j] = 1.0;
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const double nf = (x[j] <= kLinThrD) ? x[j] * sc.c25 : 1.0 - ex[j];   // fibers:247-252
+            f.v[j] = nf * cpf[j];                                                  // fibers:258
+            cpf[j] = fatigue_update<FIB == MB_FIBERS_PYMUSCLE>(cpf[j], nf, fatdt, rdidt, p.ptf);
         }
     }
     __device__ __forceinline__ void renormalise() {}
