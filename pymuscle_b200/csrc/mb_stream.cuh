@@ -114,6 +114,22 @@ __device__ __forceinline__ double k1s_unit(const K1sArgs<double>& a, const UnitD
     return F;
 }
 
+// FP64 mode, first half of a unit-step: the adapted firing rate (and the new on-duration)
+template <bool CENTRAL>
+__device__ __forceinline__ double k1s_rate(const K1sArgs<double>& a, const UnitD& p, double x, double d, double& dn,
+                                           const double* exp_tab) {
+    bool on;
+    const double r = pool_rate(p, a.sc, x, on);
+    double fr = r;
+    if (CENTRAL) {
+        const double q = fma(r, p.phir, -p.phir6);
+        const double ad = q * (1.0 - exp_neg_fast<true>(d * a.sc.mitau, exp_tab));
+        fr = r - ((ad < 0.0) ? 0.0 : ad);                               // pool:205-206, :121
+        dn = duration_update(d, r > 0.0, a.dt, a.max_dur);
+    }
+    return fr;
+}
+
 template <typename T, bool CENTRAL, bool RECOVERY, bool FORCES, bool FATIGUE, bool PERROW = false>
 __global__ void __launch_bounds__((CENTRAL ? StreamTraits<T>::kMaxWCentral : StreamTraits<T>::kMaxW) + 32,
                   CENTRAL ? StreamTraits<T>::kMinBlocksCentral : StreamTraits<T>::kMinBlocks)
@@ -311,7 +327,52 @@ k1_stream(const K1sArgs<T> a) {
                     cp += a.L;
                     if (CENTRAL) dp += a.L;
                 };
-                if (nrows == R) {
+                if constexpr (sizeof(T) == 8 && !PERROW && (CENTRAL || !FATIGUE)) {
+                    // FP64 mode: GR rows at a time in three phases, so that their FP64 chains interleave.  A
+                    // branch per row around the sigmoid's exponential (fibers_force_fast) serialises the rows --
+                    // the scheduler cannot move instructions across it, and ncu showed 40 % of the stall samples
+                    // on fixed-latency dependencies.  One branch decides for the group; rows past the end of a
+                    // partial chunk are computed on stale shared memory and not stored.  The group size is what
+                    // the register budget of the instantiation allows (measured: larger groups spill and lose; the
+                    // variant with the fatigue epilogue has no room at all and keeps the row-by-row form).
+                    constexpr int GR = CENTRAL ? 8 : 2;
+#pragma unroll
+                    for (int g = 0; g < R; g += GR) {
+                        double xr[GR], dn[GR], ex[GR];
+                        bool need = false;
+#pragma unroll
+                        for (int i = 0; i < GR; ++i) {
+                            dn[i] = d[g + i];
+                            const double fr = k1s_rate<CENTRAL>(a, p, xm[g + i], d[g + i], dn[i], exp2_tab);
+                            xr[i] = fma(c[g + i], -p.ctB, p.ctA) * fr;             // fibers:220
+                            need |= xr[i] > kLinThrD;
+                        }
+                        if (need) {
+#pragma unroll
+                            for (int i = 0; i < GR; ++i) ex[i] = exp_neg_fast<true>(-2.0 * (xr[i] * xr[i] * xr[i]), exp2_tab);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < GR; ++i) ex[i] = 1.0;
+                        }
+#pragma unroll
+                        for (int i = 0; i < GR; ++i) {
+                            const int r = g + i;
+                            const double nf = (xr[i] <= kLinThrD) ? xr[i] * a.sc.c25 : 1.0 - ex[i];   // fibers:247-252
+                            const double F = nf * c[r];                                        // fibers:258
+                            const double cn = fatigue_update<RECOVERY>(c[r], nf, fatdt, rdidt, ptf);
+                            if (nrows == R || r < nrows) {
+                                if (FORCES) *fp = F;
+                                *cp = cn;
+                                if (CENTRAL) *dp = dn[i];
+                                partial[r] += F;
+                                if (want_fatigue) csum[r] += cn;
+                            }
+                            if (FORCES) fp += a.L;
+                            cp += a.L;
+                            if (CENTRAL) dp += a.L;
+                        }
+                    }
+                } else if (nrows == R) {
 #pragma unroll
                     for (int r = 0; r < R; ++r) row(r);
                 } else {
