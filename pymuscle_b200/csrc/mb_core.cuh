@@ -83,6 +83,7 @@ struct ScalD {
 // are stored pre-multiplied by kappa.
 constexpr double kKappa = 1.4236443587288568;   // cbrt(2 * 1.4426950408889634)
 constexpr double kLinThrD = 0.4;
+constexpr double kCbrt2 = 1.2599210498948732;     // FP64 fused kernel: (cbrt(2) x)^3 = 2 x^3
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -157,7 +158,8 @@ __constant__ double kExp2Tab[32] = {
 // exp(x) for -700 <= x <= 0 in about a dozen FP64 instructions (the library exp needs ~2.5x
 // as many): x = n*ln2/32 + r, |r| <= ln2/64, exp(x) = 2^(n>>5) * 2^((n&31)/32) * P5(r).
 // Relative error < 1e-14 (truncation r^6/720 = 2e-15, two-step reduction); the FP64 mode's
-// bar is 1e-9.  `tab` is a shared-memory copy of kExp2Tab (divergent index).
+// bar is 1e-9.  (A degree-4 polynomial would still meet the bar but measured no faster: the
+// FP64 kernels are bound by latency and issue, not by the FP64 instruction count.)  `tab` is a shared-memory copy of kExp2Tab (divergent index).
 template <bool CLAMP>
 __device__ __forceinline__ double exp_neg_fast(double x, const double* tab) {
     if (CLAMP) x = fmax(x, -700.0);                                     // (the launcher proves it redundant for most tables)

@@ -389,8 +389,10 @@ struct CoreF64 {
     static constexpr bool kCentral = CENTRAL != 0;
     UnitD p;
     ScalD sc;
-    double fatdt, rdidt, dt, max_dur, decay, Emax;
-    double cpf[U], dur[U], E[U];
+    double fatdt, rdidt, dt, max_dur, decay, omd /* 1 - decay */, Gmax;
+    double c25s;                 // slope of the linear part over cbrt(2)
+    double ctA2, ctB2;           // contraction-time factors times cbrt(2): (cbrt(2) x)^3 = 2 x^3 without a multiply
+    double cpf[U], dur[U], G[U]; // G = 1 - exp(-dur/tau), the adaptation factor (pool:217-219)
     int cnt[U];                  // CENTRAL == 1: on-steps since the window started (dur[] stays at its start value)
     const double* tab;           // shared-memory copy of kExp2Tab
 
@@ -402,7 +404,11 @@ struct CoreF64 {
         dt = a.dt;
         max_dur = a.max_dur;
         decay = a.decay_d;
-        Emax = CENTRAL ? exp(a.max_dur * a.sd.mitau) : 0.0;
+        omd = -expm1(a.dt * a.sd.mitau);
+        Gmax = CENTRAL ? -expm1(a.max_dur * a.sd.mitau) : 0.0;
+        ctA2 = p.ctA * kCbrt2;
+        ctB2 = p.ctB * kCbrt2;
+        c25s = a.sd.c25 / kCbrt2;
 #pragma unroll
         for (int j = 0; j < U; ++j) init(j, a, p.ptf, 0.0);                // instances beyond the batch rest
     }
@@ -411,17 +417,17 @@ struct CoreF64 {
         cpf[j] = c;
         dur[j] = d0;
         cnt[j] = 0;
-        E[j] = CENTRAL ? exp(d0 * sc.mitau) : 1.0;                         // pool:217-218
+        G[j] = CENTRAL ? -expm1(d0 * sc.mitau) : 0.0;                      // pool:217-218
     }
-    // Fast path: E = exp(-dur/tau) is carried by the recurrence alone for the whole window -- every on-step
-    // multiplies it by exp(-dt/tau), half an ulp of relative error each, i.e. ~1e-13 after 1,000 steps against the
+    // Fast path: G = 1 - exp(-dur/tau) is carried by the recurrence alone for the whole window -- every on-step
+    // maps it to G * decay + (1 - decay), decay = exp(-dt/tau), half an ulp of relative error each, i.e. ~1e-13 after 1,000 steps against the
     // mode's 1e-9 bar -- and the duration is the start value plus an integer count of on-steps (the reference's
     // min(dur + dt, max) per on-step, pool:196-203, is monotone, so the clamp can wait until the state is stored).
     // General path: resynchronised with a full-precision exp at every tile start.
     __device__ __forceinline__ void begin_tile() {
         if (CENTRAL == 2) {
 #pragma unroll
-            for (int j = 0; j < U; ++j) E[j] = exp(dur[j] * sc.mitau);     // pool:217-218
+            for (int j = 0; j < U; ++j) G[j] = -expm1(dur[j] * sc.mitau);  // pool:217-218
         }
     }
     // CENTRAL: 0 = no adaptation, 2 = general, 1 = fast path (as in FP32 mode): the launcher has
@@ -436,10 +442,10 @@ struct CoreF64 {
             on = !(r0 < sc.min_rate);                                      // pool:171
             r = fmin(r0 * sc.gain, p.peak);                                // pool:173, :176-177
             const double q = fma(r, p.phir, -p.phir6);                     // pool:231-232
-            fr = on ? fma(-q, 1.0 - E[j], r) : 0.0;                        // pool:217-221, :121 (dur BEFORE the update)
+            fr = on ? fma(-q, G[j], r) : 0.0;                              // pool:217-221, :121 (dur BEFORE the update)
             if (on) {
                 cnt[j] += 1;
-                E[j] *= decay;
+                G[j] = fma(G[j], decay, omd);
             }
         } else {
             r = pool_rate(p, sc, e, on);
@@ -447,13 +453,13 @@ struct CoreF64 {
         }
         if (CENTRAL == 2) {
             const double q = fma(r, p.phir, -p.phir6);                     // pool:231-232
-            const double ad = q * (1.0 - E[j]);                            // pool:217-219 (dur BEFORE the update)
+            const double ad = q * G[j];                                    // pool:217-219 (dur BEFORE the update)
             fr = r - ((ad < 0.0) ? 0.0 : ad);                              // pool:221, :121
             if (r > 0.0) {                                                 // pool:196-197
                 const double dn = dur[j] + dt;
                 const bool clamp = dn > max_dur;                           // pool:202-203
                 dur[j] = clamp ? max_dur : dn;
-                E[j] = clamp ? Emax : E[j] * decay;
+                G[j] = clamp ? Gmax : fma(G[j], decay, omd);
             }
         }
         return fr;
@@ -472,20 +478,20 @@ struct CoreF64 {
             bool on;
             const double fr = rate(j, e.v[j], on);
             onbits |= (on ? 1u : 0u) << j;
-            x[j] = fma(cpf[j], -p.ctB, p.ctA) * fr;                        // fibers:220 with the fatigued contraction time
-            need |= x[j] > kLinThrD;
+            x[j] = fma(cpf[j], -ctB2, ctA2) * fr;                          // cbrt(2) * (fibers:220 with the fatigued contraction time)
+            need |= x[j] > kLinThrD * kCbrt2;
         }
         double ex[U];
         if (need) {
 #pragma unroll
-            for (int j = 0; j < U; ++j) ex[j] = exp_neg_fast<CENTRAL != 1>(-2.0 * (x[j] * x[j] * x[j]), tab);
+            for (int j = 0; j < U; ++j) ex[j] = exp_neg_fast<CENTRAL != 1>(-(x[j] * x[j]) * x[j], tab);   // exp(-2 x^3)
         } else {
 #pragma unroll
             for (int j = 0; j < U; ++j) ex[j] = 1.0;
         }
 #pragma unroll
         for (int j = 0; j < U; ++j) {
-            const double nf = (x[j] <= kLinThrD) ? x[j] * sc.c25 : 1.0 - ex[j];   // fibers:247-252
+            const double nf = (x[j] <= kLinThrD * kCbrt2) ? x[j] * c25s : 1.0 - ex[j];   // fibers:247-252
             f.v[j] = nf * cpf[j];                                                  // fibers:258
             cpf[j] = fatigue_update<FIB == MB_FIBERS_PYMUSCLE>(cpf[j], nf, fatdt, rdidt, p.ptf);
         }
