@@ -472,3 +472,41 @@ def test_generic_single_step_kernel_agrees_with_the_streaming_kernel(cuda_device
         close(tb.cpu().numpy(), ta.double().cpu().numpy(), precision, total_scale(spec), f"totals step {k}")
     close(b.cpf.cpu().numpy(), a.cpf.cpu().numpy(), precision, spec.tables()["ptf"], "capacities")
     close(b.current_forces.cpu().numpy(), a.current_forces.double().cpu().numpy(), precision, spec.tables()["ptf"], "forces")
+
+
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_many_identical_rows_give_identical_results(cuda_device, precision):
+    """The streaming kernel's work-item cursor (blocks stride through (chunk, segment) pairs without a
+    division) and the per-row alignment shifts, at a size where every block walks many items: all rows
+    get the same excitations, so every row must reproduce row 0 bit for bit, and row 0 the oracle.
+    Uniform odd layout (4,099 rows x 1,999 units) and the ragged arm (1,003 rows x 30 muscles)."""
+    rng = np.random.default_rng(23)
+    # uniform, odd row length, odd row count
+    from pymuscle_b200.tables import fibers_tables
+    base = MuscleSpec.standard()
+    n, rows = 1999, 4099
+    spec = MuscleSpec(n, base.pool, base.fibers, input_scale=base.input_scale,
+                      output_divisor=sum(fibers_tables(n, base.fibers)[0]), name="standard")
+    b, ora = MuscleBatch(spec, rows, cuda_device, precision), OracleMuscles(n, 1, "standard")
+    for k in range(4):
+        e = float(np.float32(rng.random()))                   # representable in both modes
+        tot = b.step(torch.full((rows,), e, device=cuda_device, dtype=b.dtype), 0.1)
+        want = ora.step(np.array([e]), 0.1)
+        assert torch.equal(tot, tot[:1].expand(rows))
+        assert torch.equal(b.cpf, b.cpf[:1].expand(rows, n)) and torch.equal(b.current_forces, b.current_forces[:1].expand(rows, n))
+        close(tot[:1].cpu().numpy(), want.total, precision, 1.0, f"uniform totals step {k}")
+    close(b.cpf[0].cpu().numpy(), ora.cpf[0], precision, spec.tables()["ptf"], "uniform capacities")
+    del b
+    # ragged arm
+    g = golden("arm")
+    specs = [MuscleSpec.standard(max_force=float(f)) for f in g["max_forces"]]
+    rows = 1003
+    b = MuscleBatch(specs, rows, cuda_device, precision)
+    ptf = np.concatenate([s.tables()["ptf"] for s in specs])
+    for k in range(g["exc"].shape[0]):
+        x = torch.from_numpy(np.repeat(g["exc"][k][None], rows, 0)).to(cuda_device, b.dtype)
+        tot, fat = b.step_env(x, float(g["dt"]))
+        assert torch.equal(tot, tot[:1].expand(rows, 30)) and torch.equal(fat, fat[:1].expand(rows, 30))
+        close(tot[0].cpu().numpy(), g["totals"][k], precision, 1.0, f"arm totals step {k}")
+    assert torch.equal(b.cpf, b.cpf[:1].expand(rows, b.L))
+    close(b.cpf[0].cpu().numpy(), g["cpf"], precision, ptf, "arm capacities")
