@@ -63,3 +63,39 @@ class MuscleGroupEnv:
             self._prev_len = cur.clone()
         out, fat = self.batch.step_env(a, step_size, gain=gain, want_fatigue=True)
         return out.view(self.agents, self.S), fat.view(self.agents, self.S)
+
+    def graphed_step(self, step_size: float, with_gain: bool = False):
+        """Capture one env step (the ``mb_step_env`` launch and, with ``with_gain``, the multiplication by a
+        caller-supplied per-muscle gain) in a CUDA graph and return ``f(actions, gain=None) -> (outputs,
+        fatigue)`` that replays it.  Small environments (a hopper's 4 muscles x a few hundred agents) are
+        launch-bound: a replay costs one ``cudaGraphLaunch`` instead of the Python + ctypes + allocator path.
+        The returned tensors are the graph's static outputs: they are overwritten by the next call."""
+        dev = self.device
+        a_in = torch.zeros(self.agents, self.S, dtype=self.dtype, device=dev)
+        g_in = torch.ones(self.agents, self.S, dtype=self.dtype, device=dev) if with_gain else None
+        cur = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(dev)
+        state = self.batch.state_dict()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):                       # warm-up off the capture: function attributes, occupancy cache
+            for _ in range(2):
+                self.batch.step_env(a_in, step_size, gain=g_in, want_fatigue=True)
+        cur.wait_stream(side)
+        self.batch.load_state_dict(state)                   # the warm-up steps must not count
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out, fat = self.batch.step_env(a_in, step_size, gain=g_in, want_fatigue=True)
+        self.batch.load_state_dict(state)                   # (capture does not execute, but keep the contract obvious)
+        out, fat = out.view(self.agents, self.S), fat.view(self.agents, self.S)
+
+        def step(actions: torch.Tensor, gain: Optional[torch.Tensor] = None):
+            a_in.copy_(actions.reshape(self.agents, self.S), non_blocking=True)
+            if with_gain:
+                if gain is None:
+                    raise ValueError("this graph was captured with a gain input")
+                g_in.copy_(gain.reshape(self.agents, self.S), non_blocking=True)
+            graph.replay()
+            return out, fat
+
+        step.graph = graph                                   # keep the graph (and its memory pool) alive with the callable
+        return step

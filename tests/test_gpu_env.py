@@ -87,3 +87,21 @@ def test_env_step_falls_back_on_an_odd_row_length(cuda_device):
     close(out.cpu().numpy(), o.step(x, 0.05).total, "f64", 500.0, "totals")
     want_f = np.array([1 - o.cpf[i].sum() / 1.0 for i in range(9)])           # potvin: divisor 1
     np.testing.assert_allclose(fat.cpu().numpy(), want_f, rtol=1e-12)
+
+
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_graphed_env_step_replays_the_same_step(cuda_device, precision):
+    """CUDA-graph replay of the env step == the eager call, bit for bit, state included."""
+    specs = [MuscleSpec.standard(f) for f in (20.0, 32.0, 45.0, 32.0)]
+    agents = 37
+    eager, graphed = MuscleGroupEnv(specs, agents, cuda_device, precision), MuscleGroupEnv(specs, agents, cuda_device, precision)
+    f = graphed.graphed_step(0.02, with_gain=True)
+    g = torch.Generator(device=cuda_device).manual_seed(5)
+    for k in range(25):
+        a = torch.rand(agents, 4, device=cuda_device, generator=g)
+        gain = 0.5 + torch.rand(agents, 4, device=cuda_device, generator=g)
+        out_e, fat_e = eager.batch.step_env(a.to(eager.dtype), 0.02, gain=gain.to(eager.dtype))
+        out_g, fat_g = f(a, gain)
+        assert torch.equal(out_e.view(agents, 4), out_g) and torch.equal(fat_e.view(agents, 4), fat_g), f"step {k}"
+    assert torch.equal(eager.batch.cpf, graphed.batch.cpf)
+    assert torch.equal(eager.batch.current_forces, graphed.batch.current_forces)
