@@ -610,7 +610,8 @@ static int launch_k1s_variant(const K1sArgs<T>& a, int threads, int smem, int64_
     static thread_local int c_dev = -1, c_threads = -1, c_smem = -1, c_per_sm = 0;
     const int dev = current_device();
     if (c_dev != dev || c_threads != threads || c_smem != smem) {
-        if (smem > 48 * 1024) MB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        // (the 48 KB default limit covers static + dynamic shared memory; the kernel has a few hundred static bytes)
+        if (smem > 40 * 1024) MB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int q = 0;
         MB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, threads, smem));
         if (q < 1) return fail(MB_ECUDA, "k1_stream does not fit on an SM (threads %d, smem %d)", threads, smem);
@@ -856,7 +857,7 @@ extern "C" int mb_fused_geometry(const MbConfig* cfg, int64_t M, int32_t n, int3
 
 template <typename KernelT>
 static int launch_fused(KernelT kernel, const K2Args& a, const FusedGeom& g, cudaStream_t st) {
-    if (g.smem > 48 * 1024)   // opt in to large dynamic shared memory (cheap; set on every launch)
+    if (g.smem > 40 * 1024)   // opt in to large dynamic shared memory (cheap; set on every launch; static bytes count too)
         MB_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem));
     kernel<<<(unsigned)g.blocks, g.threads, g.smem, st>>>(a);
     MB_CUDA_OK(cudaGetLastError());
