@@ -393,17 +393,17 @@ class MuscleBatch:
         cur = torch.cuda.current_stream(self.device)
         if not overlap_calls:
             st["h2d"].wait_stream(cur)
-        first = not st.get("used", False)
-        st["used"] = True
-        for i, k0 in enumerate(range(0, K, chunk)):
+        seq = st.get("seq", 0)                               # sub-windows issued so far: the staging buffers alternate
+        for k0 in range(0, K, chunk):                        # ACROSS calls too (a window may hold an odd number of them)
+            i, seq = seq, seq + 1
             b, c = i & 1, min(chunk, K - k0)
-            if i >= 2 or not first:
+            if i >= 2:
                 st["h2d"].wait_event(st["run"][b])           # the last kernel that read exc[b] is done
             with torch.cuda.stream(st["h2d"]):
                 st["exc"][b][:c].copy_(exc_host[k0:k0 + c], non_blocking=True)
                 st["up"][b].record(st["h2d"])
             cur.wait_event(st["up"][b])
-            if i >= 2 or not first:
+            if i >= 2:
                 cur.wait_event(st["down"][b])                # the last copy-out of tot[b] has drained
             self.step_many(st["exc"][b][:c], step_size, out=st["tot"][b][:c])
             st["run"][b].record(cur)
@@ -411,6 +411,7 @@ class MuscleBatch:
             with torch.cuda.stream(st["d2h"]):
                 out_host[k0:k0 + c].copy_(st["tot"][b][:c], non_blocking=True)
                 st["down"][b].record(st["d2h"])
+        st["seq"] = seq
         if not overlap_calls:
             cur.wait_stream(st["d2h"])
         return out_host
