@@ -105,3 +105,37 @@ def test_graphed_env_step_replays_the_same_step(cuda_device, precision):
         assert torch.equal(out_e.view(agents, 4), out_g) and torch.equal(fat_e.view(agents, 4), fat_g), f"step {k}"
     assert torch.equal(eager.batch.cpf, graphed.batch.cpf)
     assert torch.equal(eager.batch.current_forces, graphed.batch.current_forces)
+
+
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_rows_of_small_muscles_share_column_tiles(cuda_device, precision):
+    """Rows made of many SMALL muscles: the streaming kernel packs consecutive muscles into one column
+    tile (every consumer warp inside one muscle).  Twelve muscles of 9..264 units (957 per row, odd):
+    packed groups with muscles narrower than a warp, single-muscle groups, and muscles wider than a tile;
+    per-muscle and per-unit inputs, the fatigue epilogue, 21 rows (partial chunk)."""
+    forces = [3.0, 5.0, 8.0, 10.0, 12.0, 16.0, 20.0, 32.0, 45.0, 32.0, 70.0, 5.0]
+    specs = [MuscleSpec.standard(f) for f in forces]
+    assert [s.n for s in specs] == [9, 17, 28, 36, 44, 59, 74, 120, 169, 120, 264, 17]
+    rows, S, rng = 21, len(specs), np.random.default_rng(12)
+    offs = np.cumsum([0] + [s.n for s in specs])
+    oras, oras_u = [OracleMuscles.standard(f, m=rows) for f in forces], [OracleMuscles.standard(f, m=rows) for f in forces]
+    b, bu = MuscleBatch(specs, rows, cuda_device, precision), MuscleBatch(specs, rows, cuda_device, precision)
+    for k in range(15):
+        e = rng.random((rows, S)).astype(np.float32)
+        eu = rng.random((rows, int(offs[-1]))).astype(np.float32)
+        if k % 2:
+            got, fat = b.step_env(torch.from_numpy(e).to(cuda_device, b.dtype), 0.1)
+        else:
+            got, fat = b.step(torch.from_numpy(e).to(cuda_device, b.dtype), 0.1), None
+        got_u = bu.step(torch.from_numpy(eu).to(cuda_device, b.dtype), 0.1)
+        for j, s in enumerate(specs):
+            ptf = s.tables()["ptf"]
+            want = oras[j].step(e[:, j].astype(np.float64), 0.1)
+            want_u = oras_u[j].step(eu[:, offs[j]:offs[j + 1]].astype(np.float64), 0.1)
+            close(got[:, j].cpu().numpy(), want.total, precision, 1.0, f"totals muscle {j} step {k}")
+            close(got_u[:, j].cpu().numpy(), want_u.total, precision, 1.0, f"per-unit-input totals muscle {j} step {k}")
+            close(b.current_forces[:, offs[j]:offs[j + 1]].cpu().numpy(), want.forces, precision, ptf, f"forces {j}/{k}")
+            close(b.cpf[:, offs[j]:offs[j + 1]].cpu().numpy(), oras[j].cpf, precision, ptf, f"capacities {j}/{k}")
+            close(bu.cpf[:, offs[j]:offs[j + 1]].cpu().numpy(), oras_u[j].cpf, precision, ptf, f"per-unit-input capacities {j}/{k}")
+            if fat is not None:
+                close(fat[:, j].cpu().numpy(), oras[j].peripheral_fatigue(), precision, 1.0, f"fatigue {j}/{k}")
