@@ -38,10 +38,12 @@ template <typename T> struct StreamTraits;
 // kMinBlocks / kMinBlocksCentral: resident blocks the register budget is sized for; kDefStages: ring depth.
 // FP64 mode carries twice the registers per row value: with the FP32 geometry (288 threads x 2 blocks = 96
 // registers) its consumers spilled up to 300 bytes per thread, so it runs narrower blocks with more registers
-// (128 without central fatigue, 168 with it) and a deeper ring to keep the bytes in flight.
+// (128 without central fatigue, 168 with it) and a deeper ring to keep the bytes in flight.  FP32 mode with
+// central fatigue needs 128 registers too (narrower tiles, three blocks).
 template <> struct StreamTraits<float>  { using U = UnitF; using P = float4;  using S = ScalF; static constexpr int G = kGroupsF32;
                                           static constexpr int kMaxW = 256, kMinBlocks = 2;
-                                          static constexpr int kMaxWCentral = 256, kMinBlocksCentral = 2;   // (128 x 3 blocks: no spills, +1.5 % at n = 120 only)
+                                          static constexpr int kMaxWCentral = 128, kMinBlocksCentral = 3;   // 128 registers: at 96 the central variants spill, and how much
+                                                                                                            // depends on unrelated code (16..72 bytes seen, up to 2x in time)
                                           static constexpr int kDefStages = 2; };
 template <> struct StreamTraits<double> { using U = UnitD; using P = double2; using S = ScalD; static constexpr int G = kGroupsF64;
                                           static constexpr int kMaxW = 128, kMinBlocks = 3;
