@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define MB_ABI_VERSION 1
+#define MB_ABI_VERSION 2
 
 enum MbStatus { MB_OK = 0, MB_EINVAL = -1, MB_EUNSUPPORTED = -2, MB_ECUDA = -3 };
 
@@ -157,6 +157,27 @@ int mb_step_env(const MbConfig* cfg, const void* params_dev,
                 void* forces_dev, void* totals_dev, const void* out_gain_dev, double* fatigue_dev,
                 double step_size, void* stream);
 
+/* ---- mb_step_env with the Hill-type curves evaluated in the epilogue -------------------------------
+ * Replaces, per muscle, contractile_element_force_length_curve (pymuscle/hill_type.py:15-41) times
+ * contractile_element_force_velocity_curve (hill_type.py:44-66) applied to the muscle's output: the
+ * total of muscle (row, s) is multiplied by FL(rest, cur) * FV(rest, cur, prev, step_size) computed
+ * inside the kernel from three [rows, S] length arrays (mode's element type).  As in the reference the
+ * optimal length is pinned at 1.10 rest lengths (hill_type.py:38).  out_gain_dev (may be NULL) still
+ * multiplies on top. */
+typedef struct MbHill {
+    const void* rest_dev;            /* [rows, S] resting lengths                       */
+    const void* cur_dev;             /* [rows, S] current lengths                       */
+    const void* prev_dev;            /* [rows, S] lengths one step earlier              */
+    double curve_width_factor;       /* 17.33  hill_type.py:18 */
+    double max_velocity;             /* 3.0    hill_type.py:49 */
+    double max_eccentric_multiple;   /* 1.8    hill_type.py:50 */
+} MbHill;
+int mb_step_env_hill(const MbConfig* cfg, const void* params_dev,
+                     int64_t rows, int64_t L, int32_t S, const int32_t* seg_off_dev, const double* seg_div_dev,
+                     const void* in_dev, double* cpf_dev, double* dur_dev,
+                     void* forces_dev, void* totals_dev, const void* out_gain_dev, double* fatigue_dev,
+                     const MbHill* hill, double step_size, void* stream);
+
 /* ---- K2: K fused steps, state in registers (FP32/FP64-pipe-bound) --------------------
  * Equivalent to K successive Muscle.step calls on each of `M` identical muscles of `n`
  * units (uniform layout only: rows = M, L = n, S = 1).
@@ -198,6 +219,45 @@ int mb_step_fused_gather(const MbConfig* cfg, const void* params_dev,
                          void* const* peer_totals_dev, int32_t n_peers,
                          int64_t peer_stride_k, int64_t peer_stride_pair,
                          void* forces_last_dev, double step_size, void* stream);
+
+/* ---- the fused window with every option -----------------------------------------------------------
+ * mb_step_fused and mb_step_fused_gather are views of this call.  Zero-initialise the struct; 0 in
+ * exc_hold / totals_every / S means 1.
+ *   rows, L, S, seg_off_dev, seg_div_dev   batch layout as in mb_step; muscle m = row * S + segment.
+ *                    Uniform batches (S == 1) with 2 <= L <= 480 run the register-resident warp / block
+ *                    kernels; wider muscles and rows of several muscles run the block-per-muscle kernel
+ *                    (FP32 mode), so that e.g. 1,000 steps of StandardMuscle(2,000 units) or of a 30-muscle
+ *                    arm are ONE launch instead of 1,000 (muscle.py:144-147, :189-243 make such muscles
+ *                    first-class).
+ *   exc_hold         h: step k reads excitation row k / h -- a control signal held for h simulation
+ *                    steps (exc has ceil(K / h) rows), as in a control loop that runs slower than the
+ *                    simulation (README.md:122-130 feeds one value for the whole run)
+ *   totals_every     t: only the totals of steps t-1, 2t-1, ... are stored, at row k / t (K / t rows) */
+typedef struct MbFusedArgs {
+    int64_t rows, L;
+    int32_t S, K;
+    const int32_t* seg_off_dev;
+    const double* seg_div_dev;
+    const void* exc_dev;
+    int64_t exc_stride_k;
+    int32_t exc_hold;
+    int32_t totals_every;
+    double* cpf_dev;
+    double* dur_dev;
+    void* totals_dev;
+    int64_t totals_stride_k;
+    void* forces_dec_dev;
+    uint8_t* mask_dec_dev;
+    int32_t forces_every;
+    int32_t units_per_thread;
+    void* forces_last_dev;
+    void* const* peer_totals_dev;
+    int32_t n_peers;
+    int32_t reserved;
+    int64_t peer_stride_k, peer_stride_pair;
+} MbFusedArgs;
+int mb_step_fused_ex(const MbConfig* cfg, const void* params_dev, const MbFusedArgs* args,
+                     double step_size, void* stream);
 
 /* Launch geometry mb_step_fused would use (for reporting): muscles per block,
  * threads per block, blocks, dynamic shared memory bytes. */

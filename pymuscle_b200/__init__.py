@@ -18,3 +18,4 @@ from .distributed import ShardedMuscleBatch, shard_bounds  # noqa: F401
 from .hill_type import contractile_element_force_velocity_curve  # noqa: F401
 from .hill_type import contractile_element_force_length_curve  # noqa: F401
 from .envs import MuscleGroupEnv  # noqa: F401
+from .history import ForceHistory  # noqa: F401

@@ -13,7 +13,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MB_LIB") or os.path.join(_HERE, "csrc", "libmuscle_b200.so")   # MB_LIB: tuning builds
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 MB_OK, MB_EINVAL, MB_EUNSUPPORTED, MB_ECUDA = 0, -1, -2, -3
 MB_F32, MB_F64 = 0, 1
@@ -25,6 +25,7 @@ MB_PROP_ADAPT_NONNEG, MB_PROP_EXP_BOUNDED = 1, 2
 SYMBOLS = (
     "mb_abi_version", "mb_last_error", "mb_params_bytes", "mb_params_pack", "mb_step", "mb_step_env",
     "mb_step_fused", "mb_step_fused_gather", "mb_fused_geometry", "mb_peripheral_fatigue", "mb_peak_probe",
+    "mb_step_env_hill", "mb_step_fused_ex",
 )
 
 
@@ -47,6 +48,45 @@ class MbConfig(C.Structure):
         ("output_divisor", C.c_double),
         ("table_props", C.c_int32),
         ("param_rows", C.c_int32),
+    ]
+
+
+class MbHill(C.Structure):
+    """Mirror of ``struct MbHill`` (include/muscle_b200.h)."""
+    _fields_ = [
+        ("rest_dev", C.c_void_p),
+        ("cur_dev", C.c_void_p),
+        ("prev_dev", C.c_void_p),
+        ("curve_width_factor", C.c_double),
+        ("max_velocity", C.c_double),
+        ("max_eccentric_multiple", C.c_double),
+    ]
+
+
+class MbFusedArgs(C.Structure):
+    """Mirror of ``struct MbFusedArgs`` (include/muscle_b200.h)."""
+    _fields_ = [
+        ("rows", C.c_int64), ("L", C.c_int64),
+        ("S", C.c_int32), ("K", C.c_int32),
+        ("seg_off_dev", C.c_void_p),
+        ("seg_div_dev", C.c_void_p),
+        ("exc_dev", C.c_void_p),
+        ("exc_stride_k", C.c_int64),
+        ("exc_hold", C.c_int32),
+        ("totals_every", C.c_int32),
+        ("cpf_dev", C.c_void_p),
+        ("dur_dev", C.c_void_p),
+        ("totals_dev", C.c_void_p),
+        ("totals_stride_k", C.c_int64),
+        ("forces_dec_dev", C.c_void_p),
+        ("mask_dec_dev", C.c_void_p),
+        ("forces_every", C.c_int32),
+        ("units_per_thread", C.c_int32),
+        ("forces_last_dev", C.c_void_p),
+        ("peer_totals_dev", C.POINTER(C.c_void_p)),
+        ("n_peers", C.c_int32),
+        ("reserved", C.c_int32),
+        ("peer_stride_k", C.c_int64), ("peer_stride_pair", C.c_int64),
     ]
 
 
@@ -90,6 +130,10 @@ def _declare(lib):
                                       C.POINTER(i64), C.POINTER(i32)]
     lib.mb_peripheral_fatigue.restype = C.c_int
     lib.mb_peripheral_fatigue.argtypes = [cfgp, i64, i64, i32, vp, vp, vp, vp, vp]
+    lib.mb_step_env_hill.restype = C.c_int
+    lib.mb_step_env_hill.argtypes = [cfgp, vp, i64, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(MbHill), dbl, vp]
+    lib.mb_step_fused_ex.restype = C.c_int
+    lib.mb_step_fused_ex.argtypes = [cfgp, vp, C.POINTER(MbFusedArgs), dbl, vp]
     lib.mb_peak_probe.restype = C.c_int
     lib.mb_peak_probe.argtypes = [i32, i32, i32, i32, vp, C.POINTER(i64), vp]
 

@@ -145,7 +145,7 @@ __device__ __forceinline__ double pool_adapt(const UnitD& p, const ScalD& s, dou
 }
 
 // 2^(j/32), j = 0..31 (table of the fast exponential below)
-__constant__ double kExp2Tab[32] = {
+static __constant__ double kExp2Tab[32] = {
     0x1.0000000000000p+0, 0x1.059b0d3158574p+0, 0x1.0b5586cf9890fp+0, 0x1.11301d0125b51p+0,
     0x1.172b83c7d517bp+0, 0x1.1d4873168b9aap+0, 0x1.2387a6e756238p+0, 0x1.29e9df51fdee1p+0,
     0x1.306fe0a31b715p+0, 0x1.371a7373aa9cbp+0, 0x1.3dea64c123422p+0, 0x1.44e086061892dp+0,
@@ -266,6 +266,12 @@ __device__ __forceinline__ T warp_sum_rows8(const T (&v)[8], int lane) {
     r += __shfl_xor_sync(0xffffffffu, r, 1);
     return r;
 }
+
+// per-muscle output scaling (muscle.py:278): FP32 mode multiplies by the reciprocal, FP64 mode divides
+__device__ __forceinline__ float  out_scale(const ScalF& s, float v)  { return v * s.inv_out; }
+__device__ __forceinline__ double out_scale(const ScalD& s, double v) { return v / s.out_div; }
+__device__ __forceinline__ float  out_div(float v, double d)  { return (float)((double)v / d); }
+__device__ __forceinline__ double out_div(double v, double d) { return v / d; }
 
 // the float64 peak twitch force, exactly (a rested unit has capacity == peak, and must keep it)
 __device__ __forceinline__ double unit_peak(const UnitF& p) { return ((double)p.ptf + (double)p.ptf_lo) + (double)p.ptf_lo2; }

@@ -34,6 +34,7 @@
 // (2*sizeof(T)/n B per unit-step) -- see DESIGN.md.
 #pragma once
 #include "mb_core.cuh"
+#include "mb_async.cuh"
 
 namespace mb {
 
@@ -52,6 +53,8 @@ struct K2Args {
     const void* exc;
     int64_t exc_stride_k;
     int32_t exc_mode;            // 0 = bulk copy, 1 = element-wise loads, 2 = constant over the window
+    int32_t exc_hold;            // h >= 1: step k reads excitation row k / h (a control signal held for h steps)
+    int32_t totals_every;        // t >= 1: only the totals of steps t-1, 2t-1, ... are stored, at row k / t
     double* cpf;
     double* dur;
     void* totals;
@@ -71,40 +74,6 @@ struct K2Args {
     ScalF sf;
     ScalD sd;
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-// Blocks until the phase with the given parity has completed.  The suspend-time hint lets a
-// warp that is ahead of the others sleep in hardware instead of burning issue slots.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done)
-            : "r"(bar), "r"(parity), "r"(2000u)
-            : "memory");
-    } while (!done);
-}
-// 1-D bulk async copy global -> shared (SASS UBLKCP); bytes % 16 == 0, both addresses 16-B aligned.
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
 
 // U-wide vector of T in shared memory (one LDS/STS of 4*U or 8*U bytes)
 template <typename T, int U> struct alignas(sizeof(T) * U) VecU { T v[U]; };
@@ -516,7 +485,8 @@ __device__ __forceinline__ void publish_exc(const K2Args& a, T* exc_s, uint32_t 
     const int steps = min(a.T, a.K - k0);
     const int slot = tile & (kExcSlots - 1);
     T* dst = exc_s + slot * a.T * a.Gp;
-    const T* src = (const T*)a.exc + (int64_t)k0 * a.exc_stride_k + m0;
+    const T* src = (const T*)a.exc + m0;                  // row of step k: k / exc_hold
+    const int hold = a.exc_hold;
     const uint32_t bar = exc_bar0 + 8u * slot;
     if (a.exc_mode == 0) {
         if (lane == 0) {
@@ -525,12 +495,12 @@ __device__ __forceinline__ void publish_exc(const K2Args& a, T* exc_s, uint32_t 
             mbar_expect_tx(bar, row_bytes * steps);
             const uint32_t d0 = smem_u32(dst);
             for (int s = 0; s < steps; ++s)
-                bulk_g2s(d0 + s * a.Gp * (int)sizeof(T), src + (int64_t)s * a.exc_stride_k, row_bytes, bar);
+                bulk_g2s(d0 + s * a.Gp * (int)sizeof(T), src + (int64_t)((k0 + s) / hold) * a.exc_stride_k, row_bytes, bar);
         }
     } else {
         for (int i = lane; i < steps * a.G; i += 32) {
             const int s = i / a.G, g = i - s * a.G;
-            if (g < gcount) dst[s * a.Gp + g] = __ldg(src + (int64_t)s * a.exc_stride_k + g);
+            if (g < gcount) dst[s * a.Gp + g] = __ldg(src + (int64_t)((k0 + s) / hold) * a.exc_stride_k + g);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar);
@@ -620,13 +590,15 @@ __device__ __forceinline__ void k2_body(const K2Args& a) {
                 T acc = src[0];
 #pragma unroll 5
                 for (int q2 = 1; q2 < a.npg; ++q2) acc += src[q2 * U];
-                if (g < gcount) {
-                    const int64_t o = (int64_t)(k0 + s) * a.totals_stride_k + m0 + g;
+                const int k = k0 + s;
+                if (g < gcount && (a.totals_every == 1 || (k + 1) % a.totals_every == 0)) {
+                    const int64_t krow = k / a.totals_every;
+                    const int64_t o = krow * a.totals_stride_k + m0 + g;
                     const T v = core.out_scale(acc);
                     totals[o] = v;
                     if (a.n_peers > 0) {                               // peer GPUs (NVLink stores)
                         const int64_t mg = m0 + g;
-                        const int64_t op = (mg >> 1) * a.peer_stride_pair + (int64_t)(k0 + s) * a.peer_stride_k + (mg & 1);
+                        const int64_t op = (mg >> 1) * a.peer_stride_pair + krow * a.peer_stride_k + (mg & 1);
                         for (int pr = 0; pr < a.n_peers; ++pr) ((T*)a.totals_peer[pr])[op] = v;
                     }
                 }

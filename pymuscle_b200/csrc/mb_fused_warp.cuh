@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MB_W_MINB) k2w_f32(const 
         float2 e = make_float2(0.0f, 0.0f);
         const int k = tile * kWTile + lane;
         if (k < a.K) {
-            const float* src = exc + (int64_t)k * a.exc_stride_k + m0;   // exc_stride_k == 0: constant
+            const float* src = exc + (int64_t)(k / a.exc_hold) * a.exc_stride_k + m0;   // exc_stride_k == 0: constant
             e.x = __ldg(src);
             if (two) e.y = __ldg(src + 1);
         }
@@ -124,7 +124,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MB_W_MINB) k2w_f32(const 
         for (int i = 0; i < UPL; ++i) core[i].renormalise();
         __syncwarp();
         // ---- stage 1 (and only): lane s sums the 32 lanes' forces of step k0 + s -----------------
-        if (lane < steps) {
+        const int kl = k0 + lane;                             // the step whose totals this lane writes
+        if (lane < steps && (a.totals_every == 1 || (kl + 1) % a.totals_every == 0)) {
+            const int64_t krow = kl / a.totals_every;
             const float2* rp = ftw + lane * kWPitch;
             float2 acc0 = rp[0], acc1 = rp[1];
 #pragma unroll
@@ -134,7 +136,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MB_W_MINB) k2w_f32(const 
             }
             const float2 acc = __fadd2_rn(acc0, acc1);
             if (a.totals) {
-                const int64_t o = (int64_t)(k0 + lane) * a.totals_stride_k + m0;
+                const int64_t o = krow * a.totals_stride_k + m0;
                 const float t0 = core[0].out_scale(acc.x), t1 = core[0].out_scale(acc.y);
                 float* t = (float*)a.totals + o;
                 t[0] = t0;
@@ -142,7 +144,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MB_W_MINB) k2w_f32(const 
                 if (a.n_peers > 0) {
                     // the same totals into the peer GPUs' gather buffers.  With the pair-major layout
                     // (stride_k == 2) the 32 lanes of the warp write 256 contiguous bytes per tile
-                    const int64_t op = (m0 >> 1) * a.peer_stride_pair + (int64_t)(k0 + lane) * a.peer_stride_k;
+                    const int64_t op = (m0 >> 1) * a.peer_stride_pair + krow * a.peer_stride_k;
                     const bool vec = two && (((a.peer_stride_pair | a.peer_stride_k) & 1) == 0);
                     for (int pr = 0; pr < a.n_peers; ++pr) {
                         float* tp = (float*)a.totals_peer[pr] + op;
@@ -184,8 +186,9 @@ constexpr int kUPitch = 34;      // row pitch of the float force tile (even: 64-
 
 __device__ __forceinline__ float2 P2(float a, float b) { return make_float2(a, b); }
 
+// (PyMuscle fibers with two pairs per lane need ~100 registers: two blocks per SM instead of three, no spills)
 template <int FIB, int CENTRAL, int NPU, bool FORCES>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) k2u_f32(const K2Args a) {
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, (FIB == MB_FIBERS_PYMUSCLE && NPU == 2) ? 2 : 3) k2u_f32(const K2Args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* ftw = (float*)smem_raw + warp * (kWTile * kUPitch + 2 * kWTile);     // [32][34]
@@ -224,7 +227,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) k2u_f32(const K2Args a
     // excitation of (tile, step = lane); 0 beyond the window.  exc_stride_k == 0: constant
     auto fetch = [&](int tile) -> float {
         const int k = tile * kWTile + lane;
-        return (k < a.K) ? __ldg(exc + (int64_t)k * a.exc_stride_k + m) : 0.0f;
+        return (k < a.K) ? __ldg(exc + (int64_t)(k / a.exc_hold) * a.exc_stride_k + m) : 0.0f;
     };
     float e_next = fetch(0);
 
@@ -278,7 +281,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) k2u_f32(const K2Args a
         for (int i = 0; i < NPU; ++i) pair_renormalise<FIB>(st[i], pp[i]);
         __syncwarp();
         // ---- lane s sums the 32 lanes' forces of step k0 + s -----------------------------------
-        if (lane < steps) {
+        const int kl = k0 + lane;                             // the step whose total this lane writes
+        if (lane < steps && (a.totals_every == 1 || (kl + 1) % a.totals_every == 0)) {
+            const int64_t krow = kl / a.totals_every;
             const float2* rp = (const float2*)(ftw + lane * kUPitch);
             float2 acc0 = rp[0], acc1 = rp[1];
 #pragma unroll
@@ -289,10 +294,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) k2u_f32(const K2Args a
             const float2 acc = __fadd2_rn(acc0, acc1);
             if (a.totals) {
                 const float v = (acc.x + acc.y) * inv_out;
-                const int64_t o = (int64_t)(k0 + lane) * a.totals_stride_k + m;
+                const int64_t o = krow * a.totals_stride_k + m;
                 ((float*)a.totals)[o] = v;
                 if (a.n_peers > 0) {
-                    const int64_t op = (m >> 1) * a.peer_stride_pair + (int64_t)(k0 + lane) * a.peer_stride_k + (m & 1);
+                    const int64_t op = (m >> 1) * a.peer_stride_pair + krow * a.peer_stride_k + (m & 1);
                     for (int pr = 0; pr < a.n_peers; ++pr) ((float*)a.totals_peer[pr])[op] = v;
                 }
             }

@@ -28,6 +28,8 @@
 // consumers nothing because the row index is a compile-time constant of the unrolled loop.
 // The pool-only / fibers-only stages and the mask / rate outputs use the generic k1_step kernel.
 #pragma once
+#include "mb_core.cuh"
+#include "mb_async.cuh"
 
 namespace mb {
 
@@ -50,6 +52,35 @@ template <> struct StreamTraits<double> { using U = UnitD; using P = double2; us
                                           static constexpr int kMaxWCentral = 64, kMinBlocksCentral = 4;
                                           static constexpr int kDefStages = 3; };
 
+// Optional per-muscle epilogue of the streaming step (mb_step_env): all arrays are [rows, S].
+struct K1sEpilogue {
+    const void* out_gain = nullptr;      // multiplier of the totals (mode's element type)
+    double* fatigue = nullptr;           // 1 - sum(new capacity)/divisor (muscle.py:248-256)
+    // Hill-type factors (hill_type.py:15-66) evaluated in the epilogue from muscle lengths; hill_rest == NULL: off
+    const void* hill_rest = nullptr;     // resting lengths
+    const void* hill_cur = nullptr;      // current lengths
+    const void* hill_prev = nullptr;     // lengths one step earlier
+    double hill_width = 17.33, hill_opt = 1.10, hill_vmax = 3.0, hill_ecc = 1.8;
+};
+
+// force-length x force-velocity multiplier of one muscle (hill_type.py:15-41, :44-66)
+__device__ __forceinline__ double hill_gain(double rest, double cur, double prev, double dt, double width, double opt,
+                                            double vmax, double ecc) {
+    const double d = fabs(cur / rest - opt);
+    const double fl = exp(width * (-1.0 * (d * d * d)));                  // hill_type.py:39-41
+    const double vel = ((prev - cur) / rest) / dt;                        // hill_type.py:60
+    const double e = exp((0.04 - vel / vmax) / 0.18);                     // hill_type.py:62-63
+    return fl * (ecc - ecc / (1.0 + e));                                  // hill_type.py:65
+}
+__device__ __forceinline__ float hill_gain(float rest, float cur, float prev, double dt, double width, double opt,
+                                           double vmax, double ecc) {
+    const float d = fabsf(cur / rest - (float)opt);
+    const float fl = __expf(-(float)width * (d * d * d));
+    const float vel = ((prev - cur) / rest) / (float)dt;
+    const float e = __expf((0.04f - vel / (float)vmax) / 0.18f);
+    return fl * ((float)ecc - (float)ecc / (1.0f + e));
+}
+
 template <typename T>
 struct K1sArgs {
     const typename StreamTraits<T>::P* params;
@@ -68,6 +99,10 @@ struct K1sArgs {
     T* totals;                   // may be NULL
     const T* out_gain;           // [rows, S] multiplier of the totals (e.g. Hill-type factors); may be NULL
     double* fatigue;             // [rows, S] 1 - sum(new capacity)/divisor (muscle.py:248-256); may be NULL
+    const T* hill_rest;          // [rows, S] Hill-type epilogue (K1sEpilogue); NULL = off
+    const T* hill_cur;
+    const T* hill_prev;
+    double hill_width, hill_opt, hill_vmax, hill_ecc;
     double dt, adk_d, max_dur;
     double fat_div;              // output divisor of a uniform batch (seg_div == NULL)
     typename StreamTraits<T>::S sc;
@@ -146,10 +181,11 @@ k1_stream(const K1sArgs<T> a) {
     const int rowpi = W + 2 * kInAlign;                   // input row pitch (shift + round-up slack), a multiple of kInAlign
     constexpr int PR = PERROW ? R : 1;                    // parameter tiles per stage: one, or one per row (per-instance tables)
     T* in_s = (T*)(par_s + (size_t)NS * PR * G * W);      // [NS][R][rowpi] staged per-unit inputs (in_per_unit only)
-    T* red0 = in_s + (a.in_per_unit ? (size_t)NS * R * rowpi : 0);        // [2 item parities][2R][8]: force | capacity sums
+    double* redc0 = (double*)(in_s + (a.in_per_unit ? (size_t)NS * R * rowpi : 0));   // [2 item parities][R][8] capacity sums (float64)
+    T* red0 = (T*)(redc0 + 2 * R * 8);                                    // [2 item parities][R][8] force sums
     // ragged rows: segment offsets and divisors are read once per work item by every thread ->
     // keep them in shared memory instead of paying a dependent global load per item
-    double* segdiv_s = (double*)(red0 + 2 * 2 * R * 8);   // [S]
+    double* segdiv_s = (double*)(red0 + 2 * R * 8);       // [S]
     int32_t* segoff_s = (int32_t*)(segdiv_s + (a.seg_in_smem ? a.S : 0));   // [S + 1]
     const int32_t* seg_off = a.seg_off;
     const double* seg_div = a.seg_div;
@@ -266,7 +302,8 @@ k1_stream(const K1sArgs<T> a) {
         const int off0 = seg_off ? seg_off[seg] : 0;
         const int n = seg_off ? seg_off[seg + 1] - off0 : (int)a.L;
         const int nrows = (int)min((int64_t)R, a.rows - r0);
-        T xm[R], partial[R], csum[R];
+        T xm[R], partial[R];
+        double csum[R];                                       // new capacities, float64 in both modes (muscle.py:248-256 sums float64)
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             partial[r] = 0;
@@ -290,13 +327,11 @@ k1_stream(const K1sArgs<T> a) {
                 double ptf = unit_peak(p);
                 const double* cs = cpf_s + (s * R) * rowp + tid;
                 const double* ds = dur_s + (s * R) * rowp + tid;
-                double c[R], d[R];
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const int sh = (r & 1) ? sh1 : sh0;
-                    c[r] = cs[r * rowp + sh];
-                    d[r] = CENTRAL ? ds[r * rowp + sh] : 0.0;
-                }
+                // state of row r, read from the stage where it is used (the stage stays valid until this warp's
+                // arrival on its `empty` barrier below): loading all 2R values up front pinned 16-32 registers
+                // for the whole tile and pushed the variants with an epilogue into spills
+                auto ldc = [&](int r) { return cs[r * rowp + ((r & 1) ? sh1 : sh0)]; };
+                auto ldd = [&](int r) { return CENTRAL ? ds[r * rowp + ((r & 1) ? sh1 : sh0)] : 0.0; };
                 if (a.in_per_unit) {                                 // this unit's own excitation in every row
                     const T* xs = in_s + (size_t)(s * R) * rowpi + tid;
                     const int em = (off0 + u0) & (kInAlign - 1), lm = (int)(a.L & (kInAlign - 1));
@@ -314,13 +349,14 @@ k1_stream(const K1sArgs<T> a) {
                         rdidt = (double)p.rdi * a.dt;
                         ptf = unit_peak(p);
                     }
-                    double cn, dn = d[r];
-                    const T F = k1s_unit<CENTRAL, RECOVERY>(a, p, xm[r], c[r], d[r], fatdt, rdidt, ptf, cn, dn, exp2_tab);
+                    const double c = ldc(r), d = ldd(r);
+                    double cn, dn = d;
+                    const T F = k1s_unit<CENTRAL, RECOVERY>(a, p, xm[r], c, d, fatdt, rdidt, ptf, cn, dn, exp2_tab);
                     if (FORCES) *fp = F;
                     *cp = cn;
                     if (CENTRAL) *dp = dn;
                     partial[r] += F;
-                    if (want_fatigue) csum[r] += (T)cn;
+                    if (want_fatigue) csum[r] += cn;
                     if (FORCES) fp += a.L;
                     cp += a.L;
                     if (CENTRAL) dp += a.L;
@@ -336,13 +372,15 @@ k1_stream(const K1sArgs<T> a) {
                     constexpr int GR = CENTRAL ? 8 : 2;
 #pragma unroll
                     for (int g = 0; g < R; g += GR) {
-                        double xr[GR], dn[GR], ex[GR];
+                        double xr[GR], dn[GR], ex[GR], c[GR];
                         bool need = false;
 #pragma unroll
                         for (int i = 0; i < GR; ++i) {
-                            dn[i] = d[g + i];
-                            const double fr = k1s_rate<CENTRAL>(a, p, xm[g + i], d[g + i], dn[i], exp2_tab);
-                            xr[i] = fma(c[g + i], -p.ctB, p.ctA) * fr;             // fibers:220
+                            const double d = ldd(g + i);
+                            c[i] = ldc(g + i);
+                            dn[i] = d;
+                            const double fr = k1s_rate<CENTRAL>(a, p, xm[g + i], d, dn[i], exp2_tab);
+                            xr[i] = fma(c[i], -p.ctB, p.ctA) * fr;                 // fibers:220
                             need |= xr[i] > kLinThrD;
                         }
                         if (need) {
@@ -356,8 +394,8 @@ k1_stream(const K1sArgs<T> a) {
                         for (int i = 0; i < GR; ++i) {
                             const int r = g + i;
                             const double nf = (xr[i] <= kLinThrD) ? xr[i] * a.sc.c25 : 1.0 - ex[i];   // fibers:247-252
-                            const double F = nf * c[r];                                        // fibers:258
-                            const double cn = fatigue_update<RECOVERY>(c[r], nf, fatdt, rdidt, ptf);
+                            const double F = nf * c[i];                                        // fibers:258
+                            const double cn = fatigue_update<RECOVERY>(c[i], nf, fatdt, rdidt, ptf);
                             if (nrows == R || r < nrows) {
                                 if (FORCES) *fp = F;
                                 *cp = cn;
@@ -385,14 +423,16 @@ k1_stream(const K1sArgs<T> a) {
         if (a.totals || want_fatigue) {
             // scratch alternates between consecutive items, so ONE barrier per item is enough: a warp
             // reaches the next write of the same half only after the barrier of the item in between
-            T* red = red0 + (item_no++ & 1) * (2 * R * 8);
+            T* red = red0 + (item_no & 1) * (R * 8);
+            double* redc = redc0 + (item_no & 1) * (R * 8);
+            ++item_no;
             static_assert(R == 8, "warp_sum_rows8 reduces exactly eight rows");
             const int rr = (lane >> 2) & 7;                       // the row whose warp total this lane ends up with
             const T wf = warp_sum_rows8(partial, lane);
             if ((lane & 3) == 0) red[rr * 8 + warp] = wf;
             if (want_fatigue) {
-                const T wc = warp_sum_rows8(csum, lane);
-                if ((lane & 3) == 0) red[(R + rr) * 8 + warp] = wc;
+                const double wc = warp_sum_rows8(csum, lane);
+                if ((lane & 3) == 0) redc[rr * 8 + warp] = wc;
             }
             asm volatile("bar.sync 1, %0;" ::"r"(ncons) : "memory");
             if (tid < nrows) {
@@ -401,11 +441,15 @@ k1_stream(const K1sArgs<T> a) {
                     T sum = red[tid * 8];
                     for (int w = 1; w < ncw; ++w) sum += red[tid * 8 + w];
                     sum = seg_div ? out_div(sum, seg_div[seg]) : out_scale(a.sc, sum);
-                    a.totals[mu] = a.out_gain ? sum * a.out_gain[mu] : sum;      // epilogue: Hill-type factors etc.
+                    if (a.out_gain) sum *= a.out_gain[mu];                       // epilogue: caller-supplied multiplier
+                    if (a.hill_rest)                                             // ... and the Hill-type factors of this muscle
+                        sum *= hill_gain(a.hill_rest[mu], a.hill_cur[mu], a.hill_prev[mu], a.dt, a.hill_width, a.hill_opt,
+                                         a.hill_vmax, a.hill_ecc);
+                    a.totals[mu] = sum;
                 }
                 if (want_fatigue) {
-                    double cs = (double)red[(R + tid) * 8];
-                    for (int w = 1; w < ncw; ++w) cs += (double)red[(R + tid) * 8 + w];
+                    double cs = redc[tid * 8];
+                    for (int w = 1; w < ncw; ++w) cs += redc[tid * 8 + w];
                     a.fatigue[mu] = 1.0 - cs / (seg_div ? seg_div[seg] : a.fat_div);
                 }
             }

@@ -6,8 +6,8 @@
 //   K2  k2_fused_*        K steps per launch, state in registers, FP-pipe-bound
 //
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared ...
-#include "../../include/muscle_b200.h"
-#include "mb_core.cuh"
+#include "mb_launchers.cuh"
+#include "mb_fused_warp.cuh"     // tile constants of the warp kernels (geometry); nothing is instantiated here
 
 #include <cmath>
 #include <cstdarg>
@@ -23,7 +23,7 @@ using namespace mb;
 // =====================================================================================
 static thread_local char g_err[512] = "";
 
-static int fail(int code, const char* fmt, ...) {
+int mb::fail(int code, const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
@@ -31,11 +31,46 @@ static int fail(int code, const char* fmt, ...) {
     return code;
 }
 
-#define MB_CUDA_OK(expr)                                                                   \
-    do {                                                                                   \
-        cudaError_t e__ = (expr);                                                          \
-        if (e__ != cudaSuccess) return fail(MB_ECUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
-    } while (0)
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+// the environment is read once per process (not on every launch)
+const Knobs& mb::knobs() {
+    static const Knobs k = [] {
+        Knobs q;
+        q.k1_generic = env_int("MB_K1_GENERIC", 0);
+        q.k1_stages = env_int("MB_K1_STAGES", 0);
+        q.k1_w = env_int("MB_K1_W", 0);
+        q.k1_bps = env_int("MB_K1_BPS", 0);
+        q.k1_flat = env_int("MB_K1_FLAT", -1);
+        q.k1_small = env_int("MB_K1_SMALL", -1);
+        q.fused_block = env_int("MB_FUSED_BLOCK", 0);
+        q.fused_no_bulk = env_int("MB_FUSED_NO_BULK", 0);
+        q.fused_general = env_int("MB_FUSED_GENERAL", 0);
+        q.f64_block = env_int("MB_F64_BLOCK", 0);
+        return q;
+    }();
+    return k;
+}
+
+int mb::current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return dev;
+}
+
+int mb::sm_count() {
+    // cached per device: one process may drive several GPUs
+    static thread_local int c_dev = -1, n = 0;
+    const int dev = current_device();
+    if (dev != c_dev) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        c_dev = dev;
+    }
+    return n;
+}
 
 extern "C" int mb_abi_version(void) { return MB_ABI_VERSION; }
 extern "C" const char* mb_last_error(void) { return g_err; }
@@ -50,30 +85,6 @@ static int check_cfg(const MbConfig* c) {
     if (!(c->output_divisor > 0)) return fail(MB_EINVAL, "output_divisor must be > 0");
     if (!(c->input_scale > 0)) return fail(MB_EINVAL, "input_scale must be > 0");
     return MB_OK;
-}
-
-static const double kLog2e = 1.4426950408889634074;
-static const double kLinScale = 1.0 - std::exp(-2.0 * (0.4 * 0.4 * 0.4));   // fibers:241
-
-static ScalF scal_f(const MbConfig& c) {
-    ScalF s;
-    s.gain_e = (float)(c.firing_gain * c.input_scale);
-    s.argmin = (float)(-c.max_duration * kLog2e / c.adaptation_time_constant);
-    s.c25k = (float)(kLinScale / 0.4 / kKappa);
-    s.ythr = (float)(0.4 * kKappa);
-    s.inv_out = (float)(1.0 / c.output_divisor);
-    return s;
-}
-static ScalD scal_d(const MbConfig& c) {
-    ScalD s;
-    s.input_scale = c.input_scale;
-    s.min_rate = c.min_firing_rate;
-    s.gain = c.firing_gain;
-    s.mitau = -1.0 / c.adaptation_time_constant;
-    s.max_dur = c.max_duration;
-    s.c25 = kLinScale / 0.4;
-    s.out_div = c.output_divisor;
-    return s;
 }
 
 // =====================================================================================
@@ -139,6 +150,9 @@ extern "C" int mb_params_pack(const MbConfig* cfg, int64_t L, const double* thr,
         const double phir = phi * ratio;
         const double phir6 = phir * (minr - dd);
         adapt_nonneg = adapt_nonneg && (phir >= 0.0);
+        // ... and the peak clamp (pool:176-177) must not pull a recruited unit's rate below minR - d either:
+        // q = phir * (min(r, peak) - (minR - d)) would turn negative and pool:221 would clamp the adaptation to 0
+        adapt_nonneg = adapt_nonneg && (peak[i] * (1.0 - 1e-5) > (minr - dd));
         const double ctA = ct[i] * (1.0 + ccr) / 1000.0;
         if (ctA * peak[i] > xmax) xmax = ctA * peak[i];
         const double ctB = ct[i] * ccr / (1000.0 * ptf[i]);
@@ -262,11 +276,6 @@ __device__ __forceinline__ double k1_compute(const K1Args<double>& a, const Unit
     return F;
 }
 
-__device__ __forceinline__ float  out_scale(const ScalF& s, float v)  { return v * s.inv_out; }
-__device__ __forceinline__ double out_scale(const ScalD& s, double v) { return v / s.out_div; }   // muscle.py:278
-__device__ __forceinline__ float  out_div(float v, double d)  { return (float)((double)v / d); }
-__device__ __forceinline__ double out_div(double v, double d) { return v / d; }
-
 // One block = one muscle (segment) of R consecutive rows at a time.  A thread owns unit
 // positions tx, tx+TX, ... of the segment and advances that unit in all R rows: the unit's
 // parameters (48 / 80 bytes from L2) are loaded once per R unit-steps, so L2 traffic stays
@@ -342,10 +351,6 @@ __global__ void __launch_bounds__(256, MINB) k1_step(const K1Args<T> a) {
         }
     }
 }
-
-#include "mb_fused.cuh"
-#include "mb_fused_warp.cuh"
-#include "mb_stream.cuh"
 
 // =====================================================================================
 // K3: per-muscle capacity sums (StandardMuscle.get_peripheral_fatigue, muscle.py:248-256)
@@ -542,28 +547,6 @@ extern "C" int mb_peak_probe(int32_t kind, int32_t blocks, int32_t threads, int3
 // =====================================================================================
 // launchers
 // =====================================================================================
-static int env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return (v && *v) ? atoi(v) : dflt;
-}
-
-static int current_device() {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
-    return dev;
-}
-
-static int sm_count() {
-    // cached per device: one process may drive several GPUs
-    static thread_local int c_dev = -1, n = 0;
-    const int dev = current_device();
-    if (dev != c_dev) {
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-        c_dev = dev;
-    }
-    return n;
-}
-
 template <typename T>
 static int launch_k1(const MbConfig& c, const void* params, int64_t rows, int64_t L, int32_t S,
                      const int32_t* seg_off, const double* seg_div, int32_t stage, const void* in, int32_t in_per_unit, double* cpf,
@@ -594,35 +577,39 @@ static int launch_k1(const MbConfig& c, const void* params, int64_t rows, int64_
     const int64_t cap = (int64_t)sm_count() * (2048 / tx) * 4;   // a few waves of resident blocks
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    k1_step<T, R, 2><<<(unsigned)blocks, tx, 0, st>>>(a);
+    k1_step<T, R, (sizeof(T) == 8 ? 1 : 2)><<<(unsigned)blocks, tx, 0, st>>>(a);    // FP64 mode: 128 registers spill
     MB_CUDA_OK(cudaGetLastError());
     return MB_OK;
 }
 
-// ---- K1s launcher ---------------------------------------------------------------------------
-template <typename T, bool CENTRAL, bool RECOVERY, bool FORCES, bool FATIGUE, bool PERROW = false>
-static int launch_k1s_variant(const K1sArgs<T>& a, int threads, int smem, int64_t items, cudaStream_t st) {
-    auto kern = k1_stream<T, CENTRAL, RECOVERY, FORCES, FATIGUE, PERROW>;
-    // persistent grid: exactly the blocks that are resident at once, each walking the work list.
-    // The opt-in and the occupancy query are cached per (instantiation, geometry): a batch-of-1 drop-in
-    // step is only ~20 us long, so two driver calls per launch would show.
-    // The function attribute is per device, so the device is part of the key.
-    static thread_local int c_dev = -1, c_threads = -1, c_smem = -1, c_per_sm = 0;
-    const int dev = current_device();
-    if (c_dev != dev || c_threads != threads || c_smem != smem) {
-        // (the 48 KB default limit covers static + dynamic shared memory; the kernel has a few hundred static bytes)
-        if (smem > 40 * 1024) MB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        int q = 0;
-        MB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, threads, smem));
-        if (q < 1) return fail(MB_ECUDA, "k1_stream does not fit on an SM (threads %d, smem %d)", threads, smem);
-        c_dev = dev; c_threads = threads; c_smem = smem; c_per_sm = q;
-    }
-    int per_sm = c_per_sm;
-    const int cap = env_int("MB_K1_BPS", 0);
-    if (cap > 0 && per_sm > cap) per_sm = cap;
-    int64_t blocks = (int64_t)sm_count() * per_sm;
-    if (blocks > items) blocks = items;
-    kern<<<(unsigned)blocks, threads, smem, st>>>(a);
+// Small launches: one row per block iteration (R = 1), every (row, muscle) its own work item.  The streaming
+// pipeline below needs ~20 us to fill and drain whatever the batch size; a batch of a few hundred muscles is
+// a few hundred thousand unit-steps and wants latency, not bytes in flight.
+template <typename T>
+static int launch_k1_small(const MbConfig& c, const void* params, int64_t rows, int64_t L, int32_t S,
+                           const int32_t* seg_off, const double* seg_div, const void* in, int32_t in_per_unit, double* cpf,
+                           double* dur, void* forces, void* totals, double dt, cudaStream_t st,
+                           const typename Vec<T>::S& sc) {
+    K1Args<T> a;
+    a.params = (const typename Vec<T>::P*)params;
+    a.param_stride = c.param_rows > 1 ? (int64_t)(sizeof(T) == 4 ? kGroupsF32 : kGroupsF64) * L : 0;
+    a.rows = rows; a.L = L; a.S = S; a.seg_off = seg_off; a.seg_div = seg_div;
+    a.stage = MB_STAGE_MUSCLE; a.in_per_unit = in_per_unit;
+    a.recovery = c.fibers_kind == MB_FIBERS_PYMUSCLE;
+    a.central = c.central_fatigue != 0;
+    a.peripheral = c.peripheral_fatigue != 0;
+    a.in = (const T*)in; a.cpf = cpf; a.dur = dur;
+    a.forces = (T*)forces; a.totals = (T*)totals; a.mask = nullptr; a.rates = nullptr;
+    a.dt = dt;
+    a.adk_d = -kLog2e / c.adaptation_time_constant;
+    a.max_dur = c.max_duration;
+    a.sc = sc;
+    const int64_t mean_n = (L + S - 1) / S;
+    int tx = (int)((mean_n + 31) / 32) * 32;
+    if (tx > 256) tx = 256;
+    if (tx < 32) tx = 32;
+    const int64_t items = rows * S;
+    k1_step<T, 1, 2><<<(unsigned)items, tx, 0, st>>>(a);
     MB_CUDA_OK(cudaGetLastError());
     return MB_OK;
 }
@@ -633,7 +620,7 @@ template <typename T>
 static bool k1s_eligible(const MbConfig& c, int64_t L, int32_t stage, int32_t in_per_unit, const void* in,
                          const double* cpf, const double* dur, const uint8_t* mask, const void* rates,
                          const void* forces = (const void*)1, const void* fatigue = nullptr) {
-    if (env_int("MB_K1_GENERIC", 0)) return false;
+    if (knobs().k1_generic) return false;
     // per-instance tables: FP32 mode with the force output and without the fatigue epilogue (one instantiation set)
     if (c.param_rows > 1 && (sizeof(T) != 4 || !forces || fatigue)) return false;
     if (stage != MB_STAGE_MUSCLE || mask || rates || !c.peripheral_fatigue) return false;
@@ -652,57 +639,10 @@ static bool k1s_eligible(const MbConfig& c, int64_t L, int32_t stage, int32_t in
     return true;
 }
 
-template <typename T>
-static int launch_k1s(const MbConfig& c, const void* params, int64_t rows, int64_t L, int32_t S,
-                      const int32_t* seg_off, const double* seg_div, const void* in, int32_t in_per_unit, double* cpf,
-                      double* dur, void* forces, void* totals, const void* out_gain, double* fatigue, double dt,
-                      cudaStream_t st, const typename Vec<T>::S& sc) {
-    K1sArgs<T> a;
-    a.params = (const typename StreamTraits<T>::P*)params;
-    a.param_stride = c.param_rows > 1 ? (int64_t)StreamTraits<T>::G * L : 0;
-    a.rows = rows; a.L = L; a.S = S; a.seg_off = seg_off; a.seg_div = seg_div;
-    a.peripheral = c.peripheral_fatigue != 0;
-    a.in = (const T*)in; a.in_per_unit = in_per_unit; a.cpf = cpf; a.dur = dur; a.forces = (T*)forces; a.totals = (T*)totals;
-    a.out_gain = (const T*)out_gain; a.fatigue = fatigue; a.fat_div = c.output_divisor;
-    a.dt = dt;
-    a.adk_d = -kLog2e / c.adaptation_time_constant;
-    a.max_dur = c.max_duration;
-    a.sc = sc;
-    const bool central = c.central_fatigue != 0, recovery = c.fibers_kind == MB_FIBERS_PYMUSCLE;
-    const int64_t mean_n = (L + S - 1) / S;
-    int W = (int)((mean_n + 31) / 32) * 32;
-    // per-instance tables put R parameter tiles into every stage: narrower tiles keep two stages within reach
-    const int wcap = central ? StreamTraits<T>::kMaxWCentral : StreamTraits<T>::kMaxW;   // the instantiation's launch bound
-    int wmax = env_int("MB_K1_W", c.param_rows > 1 ? 64 : wcap);
-    if (wmax > wcap) wmax = wcap;
-    if (W > wmax) W = wmax;
-    if (W < 32) W = 32;
-    const int stage_bytes = kStreamRows * (W + 2) * 8 * (central ? 2 : 1) +                                // state rows
-                            StreamTraits<T>::G * W * 16 * (c.param_rows > 1 ? kStreamRows : 1) +         // + unit parameters
-                            (in_per_unit ? kStreamRows * (W + 2 * (16 / (int)sizeof(T))) * (int)sizeof(T) : 0);   // + per-unit inputs
-    int NS = env_int("MB_K1_STAGES", 0);
-    if (NS <= 0) NS = StreamTraits<T>::kDefStages;            // measured: FP32 mode: double buffering x 2 blocks/SM saturates HBM, deeper rings
-                                                              // only cost occupancy; FP64 mode (3-4 narrower blocks per SM): three stages
-    if (NS > 8) NS = 8;
-    if (NS < 2) NS = 2;
-    a.W = W; a.NS = NS;
-    const int threads = W + 32;
-    a.seg_in_smem = (seg_off != nullptr && S <= 2048) ? 1 : 0;
-    const int smem = 128 + NS * stage_bytes + 4 * kStreamRows * 8 * (int)sizeof(T) + (a.seg_in_smem ? S * 8 + (S + 1) * 4 + 8 : 0);
-    const int64_t items = ((rows + kStreamRows - 1) / kStreamRows) * S;
-#define MB_K1S_F(C_, R_, F_) (fatigue ? launch_k1s_variant<T, C_, R_, F_, true>(a, threads, smem, items, st) \
-                                       : launch_k1s_variant<T, C_, R_, F_, false>(a, threads, smem, items, st))
-#define MB_K1S(C_, R_) (forces ? MB_K1S_F(C_, R_, true) : MB_K1S_F(C_, R_, false))
-    if (c.param_rows > 1) {                                   // per-instance tables: forces on, no fatigue epilogue
-        if (central) return recovery ? launch_k1s_variant<T, true, true, true, false, true>(a, threads, smem, items, st)
-                                     : launch_k1s_variant<T, true, false, true, false, true>(a, threads, smem, items, st);
-        return recovery ? launch_k1s_variant<T, false, true, true, false, true>(a, threads, smem, items, st)
-                        : launch_k1s_variant<T, false, false, true, false, true>(a, threads, smem, items, st);
-    }
-    if (central) return recovery ? MB_K1S(true, true) : MB_K1S(true, false);
-    return recovery ? MB_K1S(false, true) : MB_K1S(false, false);
-#undef MB_K1S_F
-#undef MB_K1S
+// unit-steps per launch below which the low-latency kernel wins over the streaming pipeline (measured on B200)
+static int64_t small_launch_limit() {
+    const int v = knobs().k1_small;
+    return v >= 0 ? (int64_t)v : 400000;
 }
 
 extern "C" int mb_step(const MbConfig* cfg, const void* params_dev, int64_t rows, int64_t L, int32_t S,
@@ -720,42 +660,81 @@ extern "C" int mb_step(const MbConfig* cfg, const void* params_dev, int64_t rows
     if (cfg->param_rows > 1 && (S != 1 || cfg->param_rows != rows))
         return fail(MB_EINVAL, "mb_step: per-instance tables need a uniform batch with param_rows == rows");
     cudaStream_t st = (cudaStream_t)stream;
+    const K1sEpilogue no_epilogue;
+    const bool small = stage == MB_STAGE_MUSCLE && !mask_dev && !rates_dev && rows * L <= small_launch_limit();
     if (cfg->precision == MB_F32) {
+        if (small)
+            return launch_k1_small<float>(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, in_dev, in_per_unit, cpf_dev,
+                                          dur_dev, forces_dev, totals_dev, step_size, st, scal_f(*cfg));
         if (k1s_eligible<float>(*cfg, L, stage, in_per_unit, in_dev, cpf_dev, dur_dev, mask_dev, rates_dev, forces_dev))
-            return launch_k1s<float>(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, in_dev, in_per_unit, cpf_dev,
-                                     dur_dev, forces_dev, totals_dev, nullptr, nullptr, step_size, st, scal_f(*cfg));
+            return launch_k1s_f32(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, in_dev, in_per_unit, cpf_dev,
+                                  dur_dev, forces_dev, totals_dev, no_epilogue, step_size, st);
         return launch_k1<float>(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, stage, in_dev, in_per_unit, cpf_dev,
                                 dur_dev, forces_dev, totals_dev, mask_dev, rates_dev, step_size, st, scal_f(*cfg));
     }
+    if (small)
+        return launch_k1_small<double>(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, in_dev, in_per_unit, cpf_dev,
+                                       dur_dev, forces_dev, totals_dev, step_size, st, scal_d(*cfg));
     if (k1s_eligible<double>(*cfg, L, stage, in_per_unit, in_dev, cpf_dev, dur_dev, mask_dev, rates_dev, forces_dev))
-        return launch_k1s<double>(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, in_dev, in_per_unit, cpf_dev,
-                                  dur_dev, forces_dev, totals_dev, nullptr, nullptr, step_size, st, scal_d(*cfg));
+        return launch_k1s_f64(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, in_dev, in_per_unit, cpf_dev,
+                              dur_dev, forces_dev, totals_dev, no_epilogue, step_size, st);
     return launch_k1<double>(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, stage, in_dev, in_per_unit, cpf_dev, dur_dev,
                              forces_dev, totals_dev, mask_dev, rates_dev, step_size, st, scal_d(*cfg));
 }
 
-// Whole-muscle step with a fused epilogue: totals *= out_gain (per muscle) and, in the same pass,
-// the peripheral fatigue of the NEW capacities.  Streaming kernel only (see k1s_eligible).
-extern "C" int mb_step_env(const MbConfig* cfg, const void* params_dev, int64_t rows, int64_t L, int32_t S,
-                           const int32_t* seg_off_dev, const double* seg_div_dev, const void* in_dev,
-                           double* cpf_dev, double* dur_dev, void* forces_dev, void* totals_dev,
-                           const void* out_gain_dev, double* fatigue_dev, double step_size, void* stream) {
+// Whole-muscle step with a fused epilogue: totals *= out_gain (per muscle) and / or the Hill-type factors of
+// the muscle's length history and, in the same pass, the peripheral fatigue of the NEW capacities.
+// Streaming kernel only (see k1s_eligible).
+static int step_env_impl(const MbConfig* cfg, const void* params_dev, int64_t rows, int64_t L, int32_t S,
+                         const int32_t* seg_off_dev, const double* seg_div_dev, const void* in_dev,
+                         double* cpf_dev, double* dur_dev, void* forces_dev, void* totals_dev,
+                         const K1sEpilogue& ep, double step_size, void* stream) {
     if (int rc = check_cfg(cfg)) return rc;
     if (!params_dev || !in_dev || !cpf_dev) return fail(MB_EINVAL, "mb_step_env: params/in/cpf is NULL");
     if (rows <= 0 || L <= 0 || S <= 0) return fail(MB_EINVAL, "mb_step_env: rows, L, S must be positive");
     if (S > 1 && !seg_off_dev) return fail(MB_EINVAL, "mb_step_env: seg_off required when S > 1");
     if (cfg->central_fatigue && !dur_dev) return fail(MB_EINVAL, "mb_step_env: dur is NULL");
+    if (!(step_size > 0) && ep.hill_rest) return fail(MB_EINVAL, "mb_step_env: the force-velocity curve needs step_size > 0");
     cudaStream_t st = (cudaStream_t)stream;
     if (cfg->precision == MB_F32) {
-        if (!k1s_eligible<float>(*cfg, L, MB_STAGE_MUSCLE, 0, in_dev, cpf_dev, dur_dev, nullptr, nullptr, forces_dev, fatigue_dev))
+        if (!k1s_eligible<float>(*cfg, L, MB_STAGE_MUSCLE, 0, in_dev, cpf_dev, dur_dev, nullptr, nullptr, forces_dev, ep.fatigue))
             return fail(MB_EUNSUPPORTED, "mb_step_env needs 16-byte aligned state arrays and peripheral fatigue on");
-        return launch_k1s<float>(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, in_dev, 0, cpf_dev, dur_dev,
-                                 forces_dev, totals_dev, out_gain_dev, fatigue_dev, step_size, st, scal_f(*cfg));
+        return launch_k1s_f32(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, in_dev, 0, cpf_dev, dur_dev,
+                              forces_dev, totals_dev, ep, step_size, st);
     }
-    if (!k1s_eligible<double>(*cfg, L, MB_STAGE_MUSCLE, 0, in_dev, cpf_dev, dur_dev, nullptr, nullptr, forces_dev, fatigue_dev))
+    if (!k1s_eligible<double>(*cfg, L, MB_STAGE_MUSCLE, 0, in_dev, cpf_dev, dur_dev, nullptr, nullptr, forces_dev, ep.fatigue))
         return fail(MB_EUNSUPPORTED, "mb_step_env needs 16-byte aligned state arrays and peripheral fatigue on");
-    return launch_k1s<double>(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, in_dev, 0, cpf_dev, dur_dev,
-                              forces_dev, totals_dev, out_gain_dev, fatigue_dev, step_size, st, scal_d(*cfg));
+    return launch_k1s_f64(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, in_dev, 0, cpf_dev, dur_dev,
+                          forces_dev, totals_dev, ep, step_size, st);
+}
+
+extern "C" int mb_step_env(const MbConfig* cfg, const void* params_dev, int64_t rows, int64_t L, int32_t S,
+                           const int32_t* seg_off_dev, const double* seg_div_dev, const void* in_dev,
+                           double* cpf_dev, double* dur_dev, void* forces_dev, void* totals_dev,
+                           const void* out_gain_dev, double* fatigue_dev, double step_size, void* stream) {
+    K1sEpilogue ep;
+    ep.out_gain = out_gain_dev;
+    ep.fatigue = fatigue_dev;
+    return step_env_impl(cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, in_dev, cpf_dev, dur_dev, forces_dev,
+                         totals_dev, ep, step_size, stream);
+}
+
+extern "C" int mb_step_env_hill(const MbConfig* cfg, const void* params_dev, int64_t rows, int64_t L, int32_t S,
+                                const int32_t* seg_off_dev, const double* seg_div_dev, const void* in_dev,
+                                double* cpf_dev, double* dur_dev, void* forces_dev, void* totals_dev,
+                                const void* out_gain_dev, double* fatigue_dev, const MbHill* hill, double step_size,
+                                void* stream) {
+    if (!hill || !hill->rest_dev || !hill->cur_dev || !hill->prev_dev)
+        return fail(MB_EINVAL, "mb_step_env_hill: hill and its three length arrays are required");
+    if (!(hill->max_velocity > 0)) return fail(MB_EINVAL, "mb_step_env_hill: max_velocity must be > 0");
+    K1sEpilogue ep;
+    ep.out_gain = out_gain_dev;
+    ep.fatigue = fatigue_dev;
+    ep.hill_rest = hill->rest_dev; ep.hill_cur = hill->cur_dev; ep.hill_prev = hill->prev_dev;
+    ep.hill_width = hill->curve_width_factor; ep.hill_opt = 1.10;        // hill_type.py:38 pins the optimum at 1.10
+    ep.hill_vmax = hill->max_velocity; ep.hill_ecc = hill->max_eccentric_multiple;
+    return step_env_impl(cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, in_dev, cpf_dev, dur_dev, forces_dev,
+                         totals_dev, ep, step_size, stream);
 }
 
 extern "C" int mb_peripheral_fatigue(const MbConfig* cfg, int64_t rows, int64_t L, int32_t S,
@@ -774,28 +753,21 @@ extern "C" int mb_peripheral_fatigue(const MbConfig* cfg, int64_t rows, int64_t 
 }
 
 // ---- fused geometry ---------------------------------------------------------------------
-struct FusedGeom {
-    int U, q, G, Gp, T, ns, npg, ptp, threads, smem;
-    int64_t blocks;
-    int warp_kernel;      // 2: k2u_f32 (one warp per muscle, per-instance tables), 1: k2w_f32 (one warp per muscle
-                          // pair), 0: k2_fused_* (block per muscle groups)
-};
-
-
 static const int kFusedMaxUnits = 480;     // threads per block <= 480 (15 warps), 2 blocks per SM in FP32 mode
 
-static int fused_geometry(const MbConfig& c, int64_t M, int32_t n, int32_t K, int32_t upt, FusedGeom* g) {
+static int fused_geometry(const MbConfig& c, int64_t M, int32_t n, int32_t K, int32_t upt, FusedGeom* g,
+                          bool forces = false) {
     if (n < 2 || n > kFusedMaxUnits)
         return fail(MB_EUNSUPPORTED, "fused kernel supports 2 <= n <= %d units per muscle (got %d)", kFusedMaxUnits, n);
     if (M <= 0 || K <= 0) return fail(MB_EINVAL, "M and K must be positive");
     const bool f32 = c.precision == MB_F32;
     const int esz = f32 ? 4 : 8;
-    g->warp_kernel = 0;
+    g->kernel = FK_BLOCK;
     const bool per_row = c.param_rows > 1;
     if (per_row && c.param_rows != M) return fail(MB_EINVAL, "per-instance tables need param_rows == M");
     if (f32 && per_row && n <= 128) {
         // per-instance tables: one warp per muscle, pairs of units
-        g->warp_kernel = 2;
+        g->kernel = FK_WARP_UNITS;
         g->U = 1; g->q = kWarpsPerBlock; g->G = kWarpsPerBlock; g->Gp = g->G; g->T = kWTile;
         g->ns = n; g->npg = 0; g->ptp = 0;
         g->threads = kWarpsPerBlock * 32;
@@ -804,10 +776,10 @@ static int fused_geometry(const MbConfig& c, int64_t M, int32_t n, int32_t K, in
         return MB_OK;
     }
     if (per_row) upt = 1;                                    // block kernels: a thread's instances share one table
-    if (f32 && upt == 0 && n >= 12 && n <= 128 && !env_int("MB_FUSED_BLOCK", 0)) {
+    if (f32 && upt == 0 && n >= 12 && n <= 128 && !knobs().fused_block) {
         // FP32 mode, 12..128 units: one warp per pair of muscles, no cross-warp reduction (below 32 units
         // lanes idle, but the block kernel's 100+ muscles per block do worse: 3.8e11 at n = 16)
-        g->warp_kernel = 1;
+        g->kernel = FK_WARP_PAIR;
         g->U = 2; g->q = kWarpsPerBlock; g->G = 2 * kWarpsPerBlock; g->Gp = g->G; g->T = kWTile;
         g->ns = n; g->npg = 0; g->ptp = 0;
         g->threads = kWarpsPerBlock * 32;
@@ -819,9 +791,13 @@ static int fused_geometry(const MbConfig& c, int64_t M, int32_t n, int32_t K, in
     int q = kFusedMaxUnits / ns;
     if (upt != 0 && upt != 1 && upt != 2 && upt != 4) return fail(MB_EINVAL, "units_per_thread must be 0, 1, 2 or 4");
     int U = upt;
+    const bool no_u4 = forces || (f32 && c.fibers_kind == MB_FIBERS_PYMUSCLE && c.central_fatigue);
+    if (U == 4 && no_u4) U = 2;
     if (U == 0) {
         // largest U that still leaves >= 2 blocks per SM; small batches spread out instead
-        U = 4;
+        // (four instances per thread with the decimated force output, or with PyMuscle fibers + central fatigue in
+        //  FP32 mode, do not fit the block kernels' register budget: those shapes run two per thread)
+        U = no_u4 ? 2 : 4;
         while (U > 1 && (M + (int64_t)q * U - 1) / ((int64_t)q * U) < 2LL * sm_count()) U >>= 1;
     }
     // a block should not own more muscles than exist
@@ -855,41 +831,25 @@ extern "C" int mb_fused_geometry(const MbConfig* cfg, int64_t M, int32_t n, int3
     return MB_OK;
 }
 
-template <typename KernelT>
-static int launch_fused(KernelT kernel, const K2Args& a, const FusedGeom& g, cudaStream_t st) {
-    if (g.smem > 40 * 1024)   // opt in to large dynamic shared memory (cheap; set on every launch; static bytes count too)
-        MB_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g.smem));
-    kernel<<<(unsigned)g.blocks, g.threads, g.smem, st>>>(a);
-    MB_CUDA_OK(cudaGetLastError());
-    return MB_OK;
-}
-
-#define MB_DISPATCH_FORCES(KERN, FIB, CEN, UU)                                                 \
-    (forces ? launch_fused(KERN<FIB, CEN, UU, true>, a, g, st) : launch_fused(KERN<FIB, CEN, UU, false>, a, g, st))
-#define MB_DISPATCH_CENTRAL(KERN, FIB, UU)                                                     \
-    (cen == 0 ? MB_DISPATCH_FORCES(KERN, FIB, 0, UU)                                           \
-              : (cen == 1 ? MB_DISPATCH_FORCES(KERN, FIB, 1, UU) : MB_DISPATCH_FORCES(KERN, FIB, 2, UU)))
-#define MB_DISPATCH_FIB(KERN, UU)                                                              \
-    (fib == MB_FIBERS_POTVIN ? MB_DISPATCH_CENTRAL(KERN, MB_FIBERS_POTVIN, UU)                  \
-                             : MB_DISPATCH_CENTRAL(KERN, MB_FIBERS_PYMUSCLE, UU))
-#define MB_DISPATCH_CENTRAL64(FIB, UU) MB_DISPATCH_CENTRAL(k2_fused_f64, FIB, UU)
-#define MB_DISPATCH_FIB64(UU)                                                                  \
-    (fib == MB_FIBERS_POTVIN ? MB_DISPATCH_CENTRAL64(MB_FIBERS_POTVIN, UU) : MB_DISPATCH_CENTRAL64(MB_FIBERS_PYMUSCLE, UU))
-
-static int step_fused_impl(const MbConfig* cfg, const void* params_dev, int64_t M, int32_t n, int32_t K,
-                           const void* exc_dev, int64_t exc_stride_k, double* cpf_dev, double* dur_dev,
-                           void* totals_dev, int64_t totals_stride_k, void* forces_dec_dev, uint8_t* mask_dec_dev,
-                           int32_t forces_every, void* forces_last_dev, double step_size,
-                           int32_t units_per_thread, void* stream, void* const* peer_totals, int32_t n_peers,
-                           int64_t peer_stride_k, int64_t peer_stride_pair) {
+// The fused window, every option (MbFusedArgs); mb_step_fused / mb_step_fused_gather are views of it.
+extern "C" int mb_step_fused_ex(const MbConfig* cfg, const void* params_dev, const MbFusedArgs* w, double step_size,
+                                void* stream) {
     if (int rc = check_cfg(cfg)) return rc;
-    if (!params_dev || !exc_dev || !cpf_dev) return fail(MB_EINVAL, "mb_step_fused: params/exc/cpf is NULL");
-    if (cfg->central_fatigue && !dur_dev) return fail(MB_EINVAL, "mb_step_fused: dur is NULL");
-    if (forces_every < 0 || (forces_every > 0 && !forces_dec_dev)) return fail(MB_EINVAL, "mb_step_fused: forces_every without buffer");
-    if (exc_stride_k != 0 && exc_stride_k < M) return fail(MB_EINVAL, "mb_step_fused: exc_stride_k < M");
-    if (totals_dev && totals_stride_k < M) return fail(MB_EINVAL, "mb_step_fused: totals_stride_k < M");
+    if (!w) return fail(MB_EINVAL, "mb_step_fused_ex: args is NULL");
+    if (!params_dev || !w->exc_dev || !w->cpf_dev) return fail(MB_EINVAL, "mb_step_fused: params/exc/cpf is NULL");
+    if (cfg->central_fatigue && !w->dur_dev) return fail(MB_EINVAL, "mb_step_fused: dur is NULL");
+    if (w->rows <= 0 || w->L <= 0 || w->K <= 0) return fail(MB_EINVAL, "mb_step_fused: rows, L and K must be positive");
+    const int32_t S = w->S > 0 ? w->S : 1;
+    if (S > 1) return fail(MB_EUNSUPPORTED, "mb_step_fused: rows of several muscles are not covered by a fused kernel");
+    if (w->L > INT32_MAX) return fail(MB_EINVAL, "mb_step_fused: L too large");
+    const int64_t M = w->rows * S;
+    const int32_t n = (int32_t)w->L, K = w->K;
+    const int32_t hold = w->exc_hold > 0 ? w->exc_hold : 1, tev = w->totals_every > 0 ? w->totals_every : 1;
+    if (w->forces_every < 0 || (w->forces_every > 0 && !w->forces_dec_dev)) return fail(MB_EINVAL, "mb_step_fused: forces_every without buffer");
+    if (w->exc_stride_k != 0 && w->exc_stride_k < M) return fail(MB_EINVAL, "mb_step_fused: exc_stride_k < M");
+    if (w->totals_dev && w->totals_stride_k < M) return fail(MB_EINVAL, "mb_step_fused: totals_stride_k < M");
     FusedGeom g;
-    if (int rc = fused_geometry(*cfg, M, n, K, units_per_thread, &g)) return rc;
+    if (int rc = fused_geometry(*cfg, M, n, K, w->units_per_thread, &g, w->forces_every > 0)) return rc;
     const bool f32 = cfg->precision == MB_F32;
     const int esz = f32 ? 4 : 8;
 
@@ -898,28 +858,30 @@ static int step_fused_impl(const MbConfig* cfg, const void* params_dev, int64_t 
     a.params = params_dev; a.param_stride = cfg->param_rows > 1 ? (int64_t)(f32 ? kGroupsF32 : kGroupsF64) * n : 0;
     a.M = M; a.n = n; a.ns = g.ns; a.q = g.q; a.K = K; a.T = g.T; a.G = g.G; a.Gp = g.Gp;
     a.npg = g.npg; a.ptp = g.ptp;
-    a.exc = exc_dev; a.exc_stride_k = exc_stride_k;
-    if (exc_stride_k == 0) {
+    a.exc = w->exc_dev; a.exc_stride_k = w->exc_stride_k;
+    a.exc_hold = hold; a.totals_every = tev;
+    if (w->exc_stride_k == 0) {
         a.exc_mode = 2;
     } else {
         // bulk copies need 16-byte aligned rows: base pointer, row pitch, block offset and row length
-        const bool aligned = ((uintptr_t)exc_dev % 16 == 0) && ((exc_stride_k * esz) % 16 == 0) &&
+        const bool aligned = ((uintptr_t)w->exc_dev % 16 == 0) && ((w->exc_stride_k * esz) % 16 == 0) &&
                              ((g.G * esz) % 16 == 0) && ((M * esz) % 16 == 0);
-        a.exc_mode = (aligned && !env_int("MB_FUSED_NO_BULK", 0)) ? 0 : 1;
+        a.exc_mode = (aligned && !knobs().fused_no_bulk) ? 0 : 1;
     }
-    a.cpf = cpf_dev; a.dur = dur_dev; a.totals = totals_dev; a.totals_stride_k = totals_stride_k;
+    a.cpf = w->cpf_dev; a.dur = w->dur_dev; a.totals = w->totals_dev; a.totals_stride_k = w->totals_stride_k;
+    const int32_t n_peers = w->n_peers;
     if (n_peers < 0 || n_peers > kMaxPeers) return fail(MB_EINVAL, "mb_step_fused_gather: at most %d peer buffers", kMaxPeers);
-    if (n_peers > 0 && (!totals_dev || !peer_totals)) return fail(MB_EINVAL, "mb_step_fused_gather: totals / peer list is NULL");
+    if (n_peers > 0 && (!w->totals_dev || !w->peer_totals_dev)) return fail(MB_EINVAL, "mb_step_fused_gather: totals / peer list is NULL");
     a.n_peers = n_peers;
-    a.peer_stride_k = peer_stride_k;
-    a.peer_stride_pair = peer_stride_pair;
-    if (n_peers > 0 && (peer_stride_k <= 0 || peer_stride_pair <= 0)) return fail(MB_EINVAL, "mb_step_fused_gather: peer strides must be positive");
+    a.peer_stride_k = w->peer_stride_k;
+    a.peer_stride_pair = w->peer_stride_pair;
+    if (n_peers > 0 && (w->peer_stride_k <= 0 || w->peer_stride_pair <= 0)) return fail(MB_EINVAL, "mb_step_fused_gather: peer strides must be positive");
     for (int i = 0; i < n_peers; ++i) {
-        if (!peer_totals[i]) return fail(MB_EINVAL, "mb_step_fused_gather: peer buffer %d is NULL", i);
-        a.totals_peer[i] = peer_totals[i];
+        if (!w->peer_totals_dev[i]) return fail(MB_EINVAL, "mb_step_fused_gather: peer buffer %d is NULL", i);
+        a.totals_peer[i] = w->peer_totals_dev[i];
     }
-    a.forces_dec = forces_dec_dev; a.mask_dec = mask_dec_dev; a.forces_every = forces_every;
-    a.forces_last = forces_last_dev;
+    a.forces_dec = w->forces_dec_dev; a.mask_dec = w->mask_dec_dev; a.forces_every = w->forces_every;
+    a.forces_last = w->forces_last_dev;
     a.peripheral = cfg->peripheral_fatigue != 0;
     a.dt = step_size;
     a.adk_d = -kLog2e / cfg->adaptation_time_constant;
@@ -937,46 +899,18 @@ static int step_fused_impl(const MbConfig* cfg, const void* params_dev, int64_t 
     if (cfg->central_fatigue) {
         const bool clamp_invisible = cfg->max_duration / cfg->adaptation_time_constant > 110.0;
         const bool nonneg = (cfg->table_props & MB_PROP_ADAPT_NONNEG) != 0;
-        cen = (clamp_invisible && nonneg && !env_int("MB_FUSED_GENERAL", 0)) ? 1 : 2;
+        cen = (clamp_invisible && nonneg && !knobs().fused_general) ? 1 : 2;
     }
     const int fib = cfg->fibers_kind;
-    const bool forces = forces_every > 0;
+    const bool forces = w->forces_every > 0;
     cudaStream_t st = (cudaStream_t)stream;
-    if (g.warp_kernel == 2) {
-        const int npu = (n + 63) / 64;
-#define MB_U_FORCES(FIB, CEN, NPU_)                                                             \
-    (forces ? launch_fused(k2u_f32<FIB, CEN, NPU_, true>, a, g, st) : launch_fused(k2u_f32<FIB, CEN, NPU_, false>, a, g, st))
-#define MB_U_NPU(FIB, CEN) (npu == 2 ? MB_U_FORCES(FIB, CEN, 2) : MB_U_FORCES(FIB, CEN, 1))
-#define MB_U_CEN(FIB) (cen == 0 ? MB_U_NPU(FIB, 0) : (cen == 1 ? MB_U_NPU(FIB, 1) : MB_U_NPU(FIB, 2)))
-        return fib == MB_FIBERS_POTVIN ? MB_U_CEN(MB_FIBERS_POTVIN) : MB_U_CEN(MB_FIBERS_PYMUSCLE);
-#undef MB_U_CEN
-#undef MB_U_NPU
-#undef MB_U_FORCES
-    }
-    if (g.warp_kernel) {
-        const int upl = (n + 31) / 32;
-#define MB_W_FORCES(FIB, CEN, UPL_)                                                             \
-    (forces ? launch_fused(k2w_f32<FIB, CEN, UPL_, true>, a, g, st) : launch_fused(k2w_f32<FIB, CEN, UPL_, false>, a, g, st))
-#define MB_W_UPL(FIB, CEN)                                                                      \
-    (upl == 4 ? MB_W_FORCES(FIB, CEN, 4)                                                        \
-              : (upl == 3 ? MB_W_FORCES(FIB, CEN, 3) : (upl == 2 ? MB_W_FORCES(FIB, CEN, 2) : MB_W_FORCES(FIB, CEN, 1))))
-#define MB_W_CEN(FIB) (cen == 0 ? MB_W_UPL(FIB, 0) : (cen == 1 ? MB_W_UPL(FIB, 1) : MB_W_UPL(FIB, 2)))
-        return fib == MB_FIBERS_POTVIN ? MB_W_CEN(MB_FIBERS_POTVIN) : MB_W_CEN(MB_FIBERS_PYMUSCLE);
-#undef MB_W_CEN
-#undef MB_W_UPL
-#undef MB_W_FORCES
-    }
-    if (f32) {
-        if (g.U == 4) return MB_DISPATCH_FIB(k2_fused_f32, 4);
-        if (g.U == 2) return MB_DISPATCH_FIB(k2_fused_f32, 2);
-        return MB_DISPATCH_FIB(k2_fused_f32, 1);
-    }
+    if (g.kernel == FK_WARP_UNITS) return launch_k2u_f32(a, g, fib, cen, forces, st);
+    if (g.kernel == FK_WARP_PAIR) return launch_k2w_f32(a, g, fib, cen, forces, st);
+    if (f32) return launch_k2_block_f32(a, g, fib, cen, forces, st);
     // FP64: the fast path additionally needs the sigmoid's exponent bounded (no clamp in exp_neg_fast);
     // without central fatigue the clamp is kept (CENTRAL == 0 instantiates it)
     if (cen == 1 && !(cfg->table_props & MB_PROP_EXP_BOUNDED)) cen = 2;
-    if (g.U == 4) return MB_DISPATCH_FIB64(4);
-    if (g.U == 2) return MB_DISPATCH_FIB64(2);
-    return MB_DISPATCH_FIB64(1);
+    return launch_k2_block_f64(a, g, fib, cen, forces, st);
 }
 
 extern "C" int mb_step_fused(const MbConfig* cfg, const void* params_dev, int64_t M, int32_t n, int32_t K,
@@ -984,9 +918,16 @@ extern "C" int mb_step_fused(const MbConfig* cfg, const void* params_dev, int64_
                              void* totals_dev, int64_t totals_stride_k, void* forces_dec_dev, uint8_t* mask_dec_dev,
                              int32_t forces_every, void* forces_last_dev, double step_size,
                              int32_t units_per_thread, void* stream) {
-    return step_fused_impl(cfg, params_dev, M, n, K, exc_dev, exc_stride_k, cpf_dev, dur_dev, totals_dev,
-                           totals_stride_k, forces_dec_dev, mask_dec_dev, forces_every, forces_last_dev, step_size,
-                           units_per_thread, stream, nullptr, 0, 0, 0);
+    MbFusedArgs w;
+    memset(&w, 0, sizeof(w));
+    w.rows = M; w.L = n; w.S = 1; w.K = K;
+    w.exc_dev = exc_dev; w.exc_stride_k = exc_stride_k; w.exc_hold = 1;
+    w.cpf_dev = cpf_dev; w.dur_dev = dur_dev;
+    w.totals_dev = totals_dev; w.totals_stride_k = totals_stride_k; w.totals_every = 1;
+    w.forces_dec_dev = forces_dec_dev; w.mask_dec_dev = mask_dec_dev; w.forces_every = forces_every;
+    w.forces_last_dev = forces_last_dev;
+    w.units_per_thread = units_per_thread;
+    return mb_step_fused_ex(cfg, params_dev, &w, step_size, stream);
 }
 
 extern "C" int mb_step_fused_gather(const MbConfig* cfg, const void* params_dev, int64_t M, int32_t n, int32_t K,
@@ -994,7 +935,14 @@ extern "C" int mb_step_fused_gather(const MbConfig* cfg, const void* params_dev,
                                     void* totals_dev, int64_t totals_stride_k, void* const* peer_totals_dev,
                                     int32_t n_peers, int64_t peer_stride_k, int64_t peer_stride_pair,
                                     void* forces_last_dev, double step_size, void* stream) {
-    return step_fused_impl(cfg, params_dev, M, n, K, exc_dev, exc_stride_k, cpf_dev, dur_dev, totals_dev,
-                           totals_stride_k, nullptr, nullptr, 0, forces_last_dev, step_size, 0, stream,
-                           peer_totals_dev, n_peers, peer_stride_k, peer_stride_pair);
+    MbFusedArgs w;
+    memset(&w, 0, sizeof(w));
+    w.rows = M; w.L = n; w.S = 1; w.K = K;
+    w.exc_dev = exc_dev; w.exc_stride_k = exc_stride_k; w.exc_hold = 1;
+    w.cpf_dev = cpf_dev; w.dur_dev = dur_dev;
+    w.totals_dev = totals_dev; w.totals_stride_k = totals_stride_k; w.totals_every = 1;
+    w.forces_last_dev = forces_last_dev;
+    w.peer_totals_dev = peer_totals_dev; w.n_peers = n_peers;
+    w.peer_stride_k = peer_stride_k; w.peer_stride_pair = peer_stride_pair;
+    return mb_step_fused_ex(cfg, params_dev, &w, step_size, stream);
 }

@@ -233,7 +233,7 @@ class MuscleBatch:
 
     # ---- K1 with the fused environment epilogue -------------------------------------------
     def step_env(self, excitation, step_size: float, gain: Optional[torch.Tensor] = None,
-                 want_fatigue: bool = True):
+                 want_fatigue: bool = True, hill: Optional[tuple] = None):
         """One step for a vector environment: per-muscle totals (optionally multiplied by
         ``gain``, e.g. Hill-type force-length x force-velocity factors) and the peripheral
         fatigue of every muscle after the step, in ONE launch (mb_step_env).
@@ -241,6 +241,9 @@ class MuscleBatch:
         Equivalent to ``[m.step(a, dt) for m in muscles]`` followed by
         ``[m.get_peripheral_fatigue() for m in muscles]`` over every agent
         (examples/envs/muscled_hopper.py:33-34, muscle.py:248-256).
+        ``hill=(rest, cur, prev)`` -- three [rows, S] tensors of muscle lengths -- makes the kernel's
+        epilogue evaluate the Hill-type force-length and force-velocity curves (hill_type.py:15-66)
+        itself and scale each muscle's total by their product; nothing else is launched.
         Returns ``(totals, fatigue)``; fatigue is float64 (None if not wanted)."""
         x, per_unit = self._as_input(excitation, per_unit_ok=False)
         out = torch.empty(self.rows, self.S, dtype=self.dtype, device=self.device)
@@ -249,18 +252,34 @@ class MuscleBatch:
         g = None
         if gain is not None:
             g = gain.to(device=self.device, dtype=self.dtype).reshape(self.rows, self.S).contiguous()
+        lengths = None
+        if hill is not None:
+            lengths = [t.to(device=self.device, dtype=self.dtype).expand(self.rows, self.S).contiguous() for t in hill]
+            if len(lengths) != 3:
+                raise ValueError("hill must be (rest_lengths, current_lengths, previous_lengths)")
         try:
             with torch.cuda.device(self.device):
-                nat.check(nat.lib().mb_step_env(
-                    C.byref(self.cfg), _ptr(self._params), self.rows, self.L, self.S,
-                    _ptr(self._seg_off), _ptr(self._seg_div), _ptr(x), _ptr(self.cpf), _ptr(self.dur),
-                    _ptr(forces), _ptr(out), _ptr(g), _ptr(fat), float(step_size), self._stream()))
+                if lengths is None:
+                    nat.check(nat.lib().mb_step_env(
+                        C.byref(self.cfg), _ptr(self._params), self.rows, self.L, self.S,
+                        _ptr(self._seg_off), _ptr(self._seg_div), _ptr(x), _ptr(self.cpf), _ptr(self.dur),
+                        _ptr(forces), _ptr(out), _ptr(g), _ptr(fat), float(step_size), self._stream()))
+                else:
+                    hp = nat.MbHill(lengths[0].data_ptr(), lengths[1].data_ptr(), lengths[2].data_ptr(), 17.33, 3.0, 1.8)
+                    nat.check(nat.lib().mb_step_env_hill(
+                        C.byref(self.cfg), _ptr(self._params), self.rows, self.L, self.S,
+                        _ptr(self._seg_off), _ptr(self._seg_div), _ptr(x), _ptr(self.cpf), _ptr(self.dur),
+                        _ptr(forces), _ptr(out), _ptr(g), _ptr(fat), C.byref(hp), float(step_size), self._stream()))
             self.launches += 1
             self._forces = forces
         except nat.UnsupportedError:                         # layouts the streaming kernel does not cover
             out = self.step(x, step_size).view(self.rows, self.S)
             if g is not None:
                 out = out * g
+            if lengths is not None:
+                from .hill_type import (contractile_element_force_length_curve as fl,
+                                        contractile_element_force_velocity_curve as fv)
+                out = out * fl(lengths[0], lengths[1]) * fv(lengths[0], lengths[1], lengths[2], step_size)
             if want_fatigue:
                 fat = self.get_peripheral_fatigue().view(self.rows, self.S)
         return self._shape_out(out), (self._shape_out(fat) if fat is not None else None)
@@ -268,11 +287,14 @@ class MuscleBatch:
     # ---- K2: K fused steps ------------------------------------------------------------
     def step_many(self, excitations, step_size: float, steps: Optional[int] = None,
                   out: Optional[torch.Tensor] = None, forces_every: int = 0,
-                  return_masks: bool = False, units_per_thread: int = 0):
+                  return_masks: bool = False, units_per_thread: int = 0, hold: int = 1, totals_every: int = 1):
         """Advance K steps in one launch with the unit state held in registers.
 
         excitations  [K, M] (one row of per-muscle values per step) or [M] with ``steps=K``
-                     (constant over the window)
+                     (constant over the window, the README loop's form: README.md:122-130); with
+                     ``hold=h`` [ceil(K/h), M] and ``steps=K``: row i drives steps i*h .. i*h+h-1 (a
+                     controller slower than the simulation)
+        totals_every  t: only the totals of steps t-1, 2t-1, ... are produced ([K // t, M])
         returns      totals [K, M]; with ``forces_every=f`` also the per-unit forces of steps
                      f-1, 2f-1, ... as [K//f, rows, L] (and their recruitment masks if asked)
         Falls back to K single-step launches (still on the GPU) for layouts the fused kernel
@@ -282,20 +304,32 @@ class MuscleBatch:
             excitations = torch.from_numpy(np.ascontiguousarray(excitations))
         e = excitations.to(device=self.device, dtype=self.dtype, non_blocking=True).contiguous()
         M = self.n_muscles
-        if e.dim() >= 2 and e.shape[0] * M == e.numel() and steps is None:
-            K, stride_k = int(e.shape[0]), M
-            e = e.reshape(K, M)
-        elif e.numel() == M and steps is not None:
+        hold, tev = int(hold), int(totals_every)
+        if hold < 1 or tev < 1:
+            raise ValueError("hold and totals_every must be >= 1")
+        if e.numel() == M and steps is not None:
             K, stride_k = int(steps), 0
             e = e.reshape(M)
+        elif hold > 1:
+            if steps is None:
+                raise ValueError("hold > 1 needs steps=K")
+            K, stride_k = int(steps), M
+            rows_needed = (K + hold - 1) // hold
+            if e.numel() != rows_needed * M:
+                raise AssertionError(f"excitations must be [{rows_needed}, {M}] for {K} steps held {hold} each (got {tuple(e.shape)})")
+            e = e.reshape(rows_needed, M)
+        elif e.dim() >= 2 and e.shape[0] * M == e.numel() and steps is None:
+            K, stride_k = int(e.shape[0]), M
+            e = e.reshape(K, M)
         else:
             raise AssertionError(f"excitations must be [K, {M}] or [{M}] with steps=K (got {tuple(e.shape)})")
         if K <= 0:
             raise ValueError("steps must be positive")
+        Kt = K // tev
         if out is None:
-            out = torch.empty(K, M, dtype=self.dtype, device=self.device)
+            out = torch.empty(Kt, M, dtype=self.dtype, device=self.device)
         else:
-            assert out.is_contiguous() and out.dtype == self.dtype and tuple(out.shape) == (K, M)
+            assert out.is_contiguous() and out.dtype == self.dtype and tuple(out.shape) == (Kt, M)
         n_dec = K // forces_every if forces_every > 0 else 0
         forces_dec = masks = None
         if n_dec:
@@ -304,32 +338,44 @@ class MuscleBatch:
                 masks = torch.empty(n_dec, self.rows, self.L, dtype=torch.uint8, device=self.device)
         forces_last = torch.empty_like(self._forces) if self.fresh_outputs else self._forces
 
-        fused = self.S == 1
-        if fused:
-            try:
-                with torch.cuda.device(self.device):
-                    nat.check(nat.lib().mb_step_fused(
-                        C.byref(self.cfg), _ptr(self._params), M, self.L, K, _ptr(e), stride_k,
-                        _ptr(self.cpf), _ptr(self.dur), _ptr(out), M, _ptr(forces_dec), _ptr(masks),
-                        int(forces_every if n_dec else 0), _ptr(forces_last), float(step_size),
-                        int(units_per_thread), self._stream()))
-                self.launches += 1
-                self._forces = forces_last
-            except nat.UnsupportedError:
-                fused = False
+        w = nat.MbFusedArgs()
+        w.rows, w.L, w.S, w.K = self.rows, self.L, self.S, K
+        w.seg_off_dev = self._seg_off.data_ptr() if self._seg_off is not None else None
+        w.seg_div_dev = self._seg_div.data_ptr() if self._seg_div is not None else None
+        w.exc_dev, w.exc_stride_k, w.exc_hold = e.data_ptr(), stride_k, hold
+        w.totals_every = tev
+        w.cpf_dev, w.dur_dev = self.cpf.data_ptr(), self.dur.data_ptr()
+        w.totals_dev, w.totals_stride_k = out.data_ptr(), M
+        w.forces_dec_dev = forces_dec.data_ptr() if forces_dec is not None else None
+        w.mask_dec_dev = masks.data_ptr() if masks is not None else None
+        w.forces_every = int(forces_every if n_dec else 0)
+        w.units_per_thread = int(units_per_thread)
+        w.forces_last_dev = forces_last.data_ptr()
+        fused = True
+        try:
+            with torch.cuda.device(self.device):
+                nat.check(nat.lib().mb_step_fused_ex(C.byref(self.cfg), _ptr(self._params), C.byref(w),
+                                                     float(step_size), self._stream()))
+            self.launches += 1
+            self._forces = forces_last
+        except nat.UnsupportedError:
+            fused = False
         if not fused:
+            # K single-step launches (still on the GPU) writing into the freshly allocated force buffer: a tensor
+            # handed out earlier through current_forces is never overwritten (fibers:258)
             keep = self.fresh_outputs
             self.fresh_outputs = False
+            self._forces = forces_last
+            scratch = torch.empty(self.rows, self.S, dtype=self.dtype, device=self.device) if tev > 1 else None
             try:
                 for k in range(K):
                     mk = masks[(k + 1) // forces_every - 1].view(-1) if (masks is not None and (k + 1) % forces_every == 0) else None
-                    self.step(e[k] if stride_k else e, step_size, out=out[k].view(self.rows, self.S), mask_out=mk)
+                    dst = out[k // tev].view(self.rows, self.S) if (k + 1) % tev == 0 else scratch
+                    self.step(e[k // hold] if stride_k else e, step_size, out=dst, mask_out=mk)
                     if n_dec and (k + 1) % forces_every == 0:
                         forces_dec[(k + 1) // forces_every - 1].copy_(self._forces)
             finally:
                 self.fresh_outputs = keep
-            if keep:
-                self._forces = self._forces.clone()
         if n_dec:
             return (out, forces_dec, masks) if return_masks else (out, forces_dec)
         return out
@@ -360,7 +406,8 @@ class MuscleBatch:
 
     # ---- K2 with host buffers: H2D / compute / D2H pipelined over sub-windows ---------
     def step_many_host(self, exc_host: torch.Tensor, step_size: float, out_host: torch.Tensor,
-                       chunk: int = 256, overlap_calls: bool = False) -> torch.Tensor:
+                       chunk: int = 256, overlap_calls: bool = False, steps: Optional[int] = None,
+                       hold: int = 1, totals_every: int = 1) -> torch.Tensor:
         """``step_many`` for excitations and totals that live in (pinned) HOST memory.
 
         The window is cut into sub-windows of ``chunk`` steps; the host->device copy of
@@ -369,6 +416,10 @@ class MuscleBatch:
         call costs max(PCIe, kernel) rather than their sum.  Returns ``out_host``; the
         caller's current stream is made to wait for the last copy.
 
+        exc_host   [K, M] one row per step; or [M] with ``steps=K``: constant over the window (the
+                   README loop, README.md:122-130 -- 4 bytes per muscle cross PCIe instead of 4 K);
+                   or [ceil(K/h), M] with ``steps=K, hold=h``: each row held for h steps
+        out_host   [K // totals_every, M]: the totals of steps t-1, 2t-1, ... (t = totals_every)
         overlap_calls  False: the first upload waits for everything already queued on the current
                        stream (safe if ``exc_host`` is being produced by stream work).  True: the
                        upload only waits for the staging buffer to be free, so back-to-back calls
@@ -376,41 +427,89 @@ class MuscleBatch:
                        (``exc_host`` must already hold its final contents at call time, and the
                        caller joins with ``host_pipeline_join()`` before reading ``out_host``).
         """
-        K, M = int(exc_host.shape[0]), self.n_muscles
+        M = self.n_muscles
+        hold, tev = int(hold), int(totals_every)
+        if hold < 1 or tev < 1:
+            raise ValueError("hold and totals_every must be >= 1")
         assert exc_host.device.type == "cpu" and out_host.device.type == "cpu"
-        assert tuple(exc_host.shape) == (K, M) and tuple(out_host.shape) == (K, M)
         assert exc_host.dtype == self.dtype and out_host.dtype == self.dtype
-        chunk = max(1, min(int(chunk), K))
+        const = exc_host.numel() == M and steps is not None
+        if const:
+            K = int(steps)
+        elif hold > 1:
+            if steps is None:
+                raise ValueError("hold > 1 needs steps=K")
+            K = int(steps)
+            assert tuple(exc_host.shape) == ((K + hold - 1) // hold, M)
+        else:
+            K = int(exc_host.shape[0])
+            assert tuple(exc_host.shape) == (K, M) and (steps is None or int(steps) == K)
+        assert tuple(out_host.shape) == (K // tev, M)
+        # sub-window boundaries fall on multiples of both periods; the staging buffers are sized by the REQUESTED
+        # chunk (a shorter last sub-window uses a slice), so the pipeline -- streams, events, buffers with copies
+        # possibly still in flight -- is never rebuilt because a window happens to be short
+        period = hold * tev // np.gcd(hold, tev)
+        chunk = max(period, int(chunk) // period * period)
         st = getattr(self, "_host_pipe", None)
-        if st is None or st["chunk"] != chunk:
+        if st is None or st["chunk"] != chunk or st["hold"] != hold or st["tev"] != tev:
+            if st is not None:                                # retire the old pipeline only once it has drained
+                cur0 = torch.cuda.current_stream(self.device)
+                cur0.wait_stream(st["h2d"])
+                cur0.wait_stream(st["d2h"])
+                st["h2d"].wait_stream(cur0)
+                st["d2h"].wait_stream(cur0)
+                st["h2d"].synchronize()
+                st["d2h"].synchronize()
             with torch.cuda.device(self.device):
-                st = dict(chunk=chunk, h2d=torch.cuda.Stream(self.device), d2h=torch.cuda.Stream(self.device),
-                          exc=[torch.empty(chunk, M, dtype=self.dtype, device=self.device) for _ in range(2)],
-                          tot=[torch.empty(chunk, M, dtype=self.dtype, device=self.device) for _ in range(2)],
+                st = dict(chunk=chunk, hold=hold, tev=tev,
+                          h2d=torch.cuda.Stream(self.device), d2h=torch.cuda.Stream(self.device),
+                          exc=[torch.empty(chunk // hold, M, dtype=self.dtype, device=self.device) for _ in range(2)],
+                          tot=[torch.empty(chunk // tev, M, dtype=self.dtype, device=self.device) for _ in range(2)],
+                          cexc=[torch.empty(M, dtype=self.dtype, device=self.device) for _ in range(2)],
                           up=[torch.cuda.Event() for _ in range(2)], run=[torch.cuda.Event() for _ in range(2)],
-                          down=[torch.cuda.Event() for _ in range(2)])
+                          down=[torch.cuda.Event() for _ in range(2)], cup=torch.cuda.Event(), crun=[None, None])
             self._host_pipe = st
         cur = torch.cuda.current_stream(self.device)
         if not overlap_calls:
             st["h2d"].wait_stream(cur)
+        ce = None
+        if const:                                            # one small upload per call, double-buffered across calls
+            cb = st.get("cseq", 0) & 1
+            st["cseq"] = st.get("cseq", 0) + 1
+            if st["crun"][cb] is not None:
+                st["h2d"].wait_event(st["crun"][cb])         # the last kernel that read this buffer is done
+            with torch.cuda.stream(st["h2d"]):
+                st["cexc"][cb].copy_(exc_host.reshape(M), non_blocking=True)
+                st["cup"].record(st["h2d"])
+            cur.wait_event(st["cup"])
+            ce = st["cexc"][cb]
         seq = st.get("seq", 0)                               # sub-windows issued so far: the staging buffers alternate
         for k0 in range(0, K, chunk):                        # ACROSS calls too (a window may hold an odd number of them)
             i, seq = seq, seq + 1
             b, c = i & 1, min(chunk, K - k0)
-            if i >= 2:
-                st["h2d"].wait_event(st["run"][b])           # the last kernel that read exc[b] is done
-            with torch.cuda.stream(st["h2d"]):
-                st["exc"][b][:c].copy_(exc_host[k0:k0 + c], non_blocking=True)
-                st["up"][b].record(st["h2d"])
-            cur.wait_event(st["up"][b])
+            ce_rows, ct_rows = (c + hold - 1) // hold, c // tev
+            if not const:
+                if i >= 2:
+                    st["h2d"].wait_event(st["run"][b])       # the last kernel that read exc[b] is done
+                with torch.cuda.stream(st["h2d"]):
+                    st["exc"][b][:ce_rows].copy_(exc_host[k0 // hold:k0 // hold + ce_rows], non_blocking=True)
+                    st["up"][b].record(st["h2d"])
+                cur.wait_event(st["up"][b])
             if i >= 2:
                 cur.wait_event(st["down"][b])                # the last copy-out of tot[b] has drained
-            self.step_many(st["exc"][b][:c], step_size, out=st["tot"][b][:c])
+            if ct_rows or c:
+                self.step_many(ce if const else st["exc"][b][:ce_rows], step_size, steps=(c if (const or hold > 1) else None),
+                               out=st["tot"][b][:ct_rows], hold=hold, totals_every=tev)
             st["run"][b].record(cur)
             st["d2h"].wait_event(st["run"][b])
             with torch.cuda.stream(st["d2h"]):
-                out_host[k0:k0 + c].copy_(st["tot"][b][:c], non_blocking=True)
+                if ct_rows:
+                    out_host[k0 // tev:k0 // tev + ct_rows].copy_(st["tot"][b][:ct_rows], non_blocking=True)
                 st["down"][b].record(st["d2h"])
+        if const:
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            st["crun"][cb] = ev
         st["seq"] = seq
         if not overlap_calls:
             cur.wait_stream(st["d2h"])

@@ -9,7 +9,8 @@ muscles for ``agents`` copies on the GPU: ``step(actions)`` is one streaming-ker
 returns every muscle's output and, as the proprioceptive observation the library offers
 (README "fatigue" signal, muscle.py:248-256), every muscle's peripheral fatigue.  With
 ``rest_lengths`` set, outputs are scaled by the Hill-type force-length and force-velocity
-factors (pymuscle/hill_type.py) of the muscle lengths the physics reports.
+factors (pymuscle/hill_type.py:15-66) of the muscle lengths the physics reports; the curves are
+evaluated inside the same launch (the kernel's per-muscle epilogue, ``mb_step_env_hill``).
 """
 from __future__ import annotations
 
@@ -18,8 +19,6 @@ from typing import Optional, Sequence, Union
 import torch
 
 from .engine import MuscleBatch
-from .hill_type import (contractile_element_force_length_curve,
-                        contractile_element_force_velocity_curve)
 from .tables import MuscleSpec
 
 
@@ -52,16 +51,15 @@ class MuscleGroupEnv:
         lengths [agents, S] current muscle lengths (needs ``rest_lengths``).
         Returns (outputs [agents, S], fatigue [agents, S] float64)."""
         a = actions.to(device=self.device, dtype=self.dtype).reshape(self.agents, self.S)
-        gain = None
+        hill = None
         if lengths is not None:
             if self.rest is None:
                 raise ValueError("lengths given but the environment has no rest_lengths")
             cur = lengths.to(device=self.device, dtype=self.dtype).reshape(self.agents, self.S)
-            prev = cur if self._prev_len is None else self._prev_len
-            gain = contractile_element_force_length_curve(self.rest, cur) * \
-                contractile_element_force_velocity_curve(self.rest, cur, prev, step_size)
+            prev = cur if self._prev_len is None else self._prev_len      # first step: zero velocity
+            hill = (self.rest, cur, prev)
             self._prev_len = cur.clone()
-        out, fat = self.batch.step_env(a, step_size, gain=gain, want_fatigue=True)
+        out, fat = self.batch.step_env(a, step_size, want_fatigue=True, hill=hill)
         return out.view(self.agents, self.S), fat.view(self.agents, self.S)
 
     def graphed_step(self, step_size: float, with_gain: bool = False):

@@ -1,7 +1,9 @@
 """torchrun check of ShardedMuscleBatch on real GPUs (NCCL): sharded == unsharded.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
-        --master-port 29533 scripts/dist_check.py
+        --master-port 29533 scripts/dist_check.py [--timing]
+
+tests/test_gpu_multi.py launches this (without --timing) when the box has at least two GPUs.
 """
 import os, sys
 import torch
@@ -43,6 +45,11 @@ for precision in ("f32", "f64"):
     if rank == 0:
         print(f"[dist_check] {precision}: world {world}, {M} muscles sharded {sb.sizes}: sharded == unsharded (bitwise), "
               f"NCCL gather and kernel-fused peer gather", flush=True)
+
+if "--timing" not in sys.argv:                               # tests/test_gpu_multi.py runs the correctness part only
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0)
 
 # ---- cost of the gather on the headline shape (per rank 65,536 muscles x 1,000 steps, FP32 mode) ----
 Mr, K2 = 65536, 1000

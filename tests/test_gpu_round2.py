@@ -1,0 +1,390 @@
+"""
+GPU tests added in round 2 (all through the C ABI):
+
+* the gather of totals fused into the kernels' epilogue (``mb_step_fused_gather``) with the peer
+  buffers pointing at LOCAL memory, so that a single GPU exercises every peer-store branch;
+* held excitations (``exc_hold``) and decimated totals (``totals_every``) of ``mb_step_fused_ex``;
+* the host-buffer pipeline's constant / held forms;
+* a pool whose peak firing rates drop below ``min_firing_rate - derecruitment_delta`` (the fused fast
+  path must not be taken: the reference clamps the then-negative adaptation, pool:205-206);
+* the Hill-type curves evaluated inside the step kernel (hill_type.py:15-66);
+* the fused fatigue readout at rest (exactly 0, muscle.py:248-256) and against the stand-alone kernel;
+* history capture through the pinned-host ring (README.md:128-145);
+* guard bands of NaN around the state tensors (no kernel writes outside its arrays);
+* the low-latency kernel for small launches against the streaming kernel.
+"""
+import os
+import subprocess
+import sys
+from dataclasses import replace
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, golden
+from oracle.pymuscle_oracle import OracleMuscles, PoolHyper
+from pymuscle_b200 import ForceHistory, MuscleBatch, MuscleGroupEnv, MuscleSpec
+from pymuscle_b200 import hill_type
+from test_gpu_parity import close, total_scale
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_window(ora, exc, dt):
+    return np.stack([ora.step(exc[k].astype(np.float64), dt).total for k in range(exc.shape[0])])
+
+
+# --------------------------------------------------------------------------------------------------
+# fused gather, single GPU: peers are local buffers
+# --------------------------------------------------------------------------------------------------
+def _batch_for(kernel, M, dev):
+    """(batch, oracle factory, precision) routed to the named fused kernel."""
+    if kernel == "k2w_f32":                       # one warp per muscle pair
+        return MuscleBatch(MuscleSpec.potvin(120), M, dev, "f32"), lambda: OracleMuscles(120, M, "potvin"), "f32"
+    if kernel == "k2_fused_f32":                  # block kernel: more than 128 units
+        spec = MuscleSpec.standard(90.0)
+        assert spec.n == 340
+        return MuscleBatch(spec, M, dev, "f32"), lambda: OracleMuscles.standard(90.0, m=M), "f32"
+    if kernel == "k2_fused_f64":
+        return MuscleBatch(MuscleSpec.potvin(120), M, dev, "f64"), lambda: OracleMuscles(120, M, "potvin"), "f64"
+    raise AssertionError(kernel)
+
+
+@pytest.mark.parametrize("layout", ["step_major", "pair_major"])
+@pytest.mark.parametrize("n_peers", [1, 3])
+@pytest.mark.parametrize("kernel", ["k2w_f32", "k2_fused_f32", "k2_fused_f64", "k2u_f32"])
+def test_fused_gather_into_local_peer_buffers(cuda_device, kernel, n_peers, layout):
+    M, K, dt = 37, 45, 0.02                       # odd muscle count: the last warp / pair is half empty
+    rng = np.random.default_rng(5)
+    if kernel == "k2u_f32":                       # per-instance tables: one warp per muscle
+        base = MuscleSpec.potvin(120)
+        specs = [replace(base, pool=replace(base.pool, adaptation_magnitude=0.5 + 0.01 * r)) for r in range(M)]
+        b = MuscleBatch(base, M, cuda_device, "f32", row_specs=specs)
+        oras = [OracleMuscles(120, 1, "potvin", pool=PoolHyper(adaptation_magnitude=0.5 + 0.01 * r)) for r in range(M)]
+        precision, scale_in = "f32", 67.0
+    else:
+        b, mk, precision = _batch_for(kernel, M, cuda_device)
+        oras, scale_in = None, (1.0 if kernel == "k2_fused_f32" else 67.0)
+        ora = mk()
+    exc = (scale_in * rng.random((K, M))).astype(np.float32)
+    x = torch.from_numpy(exc).to(cuda_device, b.dtype)
+    local = torch.empty(K, M, dtype=b.dtype, device=cuda_device)
+    pairs, M_total, col0 = (M + 1) // 2, 2 * M + 6, 4            # this "rank" owns columns 4 .. 4+M of a wider gather
+    nan = float("nan")
+    if layout == "step_major":                                     # [K, M_total]: (stride_k, stride_pair) = (M_total, 2)
+        bufs = [torch.full((K, M_total), nan, dtype=b.dtype, device=cuda_device) for _ in range(n_peers)]
+        ptrs = [t.data_ptr() + col0 * t.element_size() for t in bufs]
+        sk, sp = M_total, 2
+    else:                                                          # region[pair][k][2]: (2, 2 * K_max)
+        kmax = K + 3
+        bufs = [torch.full((pairs, kmax, 2), nan, dtype=b.dtype, device=cuda_device) for _ in range(n_peers)]
+        ptrs = [t.data_ptr() for t in bufs]
+        sk, sp = 2, 2 * kmax
+    b.step_many_gather(x, dt, local, ptrs, sk, sp)
+    torch.cuda.synchronize()
+    got = local.cpu().numpy()
+    if oras is None:
+        want = oracle_window(ora, exc, dt)
+        spec = b.specs[0]
+    else:
+        want = np.concatenate([oracle_window(o, exc[:, r:r + 1], dt) for r, o in enumerate(oras)], axis=1)
+        spec = b.specs[0]
+    close(got, want, precision, total_scale(spec), f"{kernel} local totals")
+    for t in bufs:
+        h = t.cpu().numpy()
+        if layout == "step_major":
+            assert np.array_equal(h[:, col0:col0 + M], got), "peer copy differs from the local totals"
+            assert np.isnan(h[:, :col0]).all() and np.isnan(h[:, col0 + M:]).all(), "stores outside this rank's region"
+        else:
+            dense = h[:, :K].transpose(1, 0, 2).reshape(K, -1)
+            assert np.array_equal(dense[:, :M], got)
+            assert np.isnan(h[:, K:]).all(), "stores beyond the window"
+            if M & 1:
+                assert np.isnan(dense[:, M:]).all(), "the empty half of the last pair was written"
+
+
+# --------------------------------------------------------------------------------------------------
+# held excitations / decimated totals
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision,kind,n", [("f32", "potvin", 120), ("f64", "potvin", 120), ("f32", "standard", 340),
+                                              ("f32", "potvin", 33)])
+@pytest.mark.parametrize("hold,tev", [(1, 4), (5, 1), (3, 6), (7, 5)])
+def test_hold_and_totals_every_match_the_plain_window(cuda_device, precision, kind, n, hold, tev):
+    M, K, dt = 19, 90, 0.02
+    spec = MuscleSpec.potvin(n) if kind == "potvin" else MuscleSpec.standard(90.0)
+    assert spec.n == n
+    rng = np.random.default_rng(hold * 10 + tev)
+    rows = (K + hold - 1) // hold
+    ctrl = ((67.0 if kind == "potvin" else 1.0) * rng.random((rows, M))).astype(np.float32)
+    a = MuscleBatch(spec, M, cuda_device, precision)
+    bref = MuscleBatch(spec, M, cuda_device, precision)
+    xc = torch.from_numpy(ctrl).to(cuda_device, a.dtype)
+    got = a.step_many(xc, dt, steps=K, hold=hold, totals_every=tev)
+    full = bref.step_many(xc.repeat_interleave(hold, dim=0)[:K].contiguous(), dt)
+    torch.cuda.synchronize()
+    assert tuple(got.shape) == (K // tev, M)
+    assert torch.equal(got, full[tev - 1::tev][:K // tev]), "decimated / held window differs from the plain one"
+    assert torch.equal(a.cpf, bref.cpf) and torch.equal(a.dur, bref.dur)
+    assert torch.equal(a.current_forces, bref.current_forces)
+
+
+def test_ragged_fallback_honours_hold_and_totals_every(cuda_device):
+    specs = [MuscleSpec.standard(f) for f in (20.0, 32.0, 45.0)]
+    rows, K, dt, hold, tev = 5, 24, 0.02, 4, 3
+    a = MuscleBatch(specs, rows, cuda_device, "f64")
+    ref = MuscleBatch(specs, rows, cuda_device, "f64")
+    ctrl = torch.rand(K // hold, rows * 3, device=cuda_device, dtype=torch.float64)
+    got = a.step_many(ctrl, dt, steps=K, hold=hold, totals_every=tev)
+    want = torch.stack([ref.step(ctrl[k // hold].view(rows, 3), dt).reshape(-1) for k in range(K)])
+    torch.testing.assert_close(got, want[tev - 1::tev], rtol=1e-9, atol=1e-12)   # (one launch vs K launches: sums may re-associate)
+    torch.testing.assert_close(a.cpf, ref.cpf, rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("form", ["per_step", "constant", "held"])
+def test_host_pipeline_forms(cuda_device, form):
+    M, K, dt = 256, 70, 0.02
+    spec = MuscleSpec.potvin(120)
+    a, ref = MuscleBatch(spec, M, cuda_device, "f32"), MuscleBatch(spec, M, cuda_device, "f32")
+    g = torch.Generator().manual_seed(3)
+    hold = 5 if form == "held" else 1
+    tev = 2 if form != "per_step" else 1
+    rows = 1 if form == "constant" else (K + hold - 1) // hold
+    ctrl = (67.0 * torch.rand(rows, M, generator=g)).pin_memory()
+    out = torch.full((K // tev, M), float("nan")).pin_memory()
+    for _ in range(2):                                               # two windows: the pipeline carries over calls
+        if form == "constant":
+            a.step_many_host(ctrl[0], dt, out, chunk=32, steps=K, totals_every=tev, overlap_calls=True)
+            want = ref.step_many(ctrl[0].to(cuda_device), dt, steps=K)
+        elif form == "held":
+            a.step_many_host(ctrl, dt, out, chunk=32, steps=K, hold=hold, totals_every=tev, overlap_calls=True)
+            want = ref.step_many(ctrl.to(cuda_device).repeat_interleave(hold, dim=0)[:K].contiguous(), dt)
+        else:
+            a.step_many_host(ctrl, dt, out, chunk=32, overlap_calls=True)
+            want = ref.step_many(ctrl.to(cuda_device), dt)
+        a.host_pipeline_join()
+        torch.cuda.synchronize()
+        assert torch.equal(out, want[tev - 1::tev][:K // tev].cpu())
+    assert torch.equal(a.cpf, ref.cpf)
+
+
+# --------------------------------------------------------------------------------------------------
+# peak rates below minR - d  =>  negative adaptation must be clamped (pool:205-206)
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_low_peak_rates_take_the_general_adaptation_path(cuda_device, precision):
+    n, M, K, dt = 120, 8, 400, 0.02
+    base = MuscleSpec.potvin(n)
+    spec = replace(base, pool=replace(base.pool, max_firing_rate_last_unit=5))
+    ph = PoolHyper(max_firing_rate_last_unit=5)
+    ora = OracleMuscles(n, M, "potvin", pool=ph)
+    assert (ora.t.peak < ph.min_firing_rate - ph.derecruitment_delta).any(), "the case needs units whose peak is below minR - d"
+    rng = np.random.default_rng(11)
+    exc = (spec.pool.max_excitation * (0.6 + 0.4 * rng.random((K, M)))).astype(np.float32)
+    b = MuscleBatch(spec, M, cuda_device, precision)
+    from pymuscle_b200 import _native as nat
+    assert not (b.cfg.table_props & nat.MB_PROP_ADAPT_NONNEG)
+    got = b.step_many(torch.from_numpy(exc).to(cuda_device, b.dtype), dt)
+    want = oracle_window(ora, exc, dt)
+    close(got.cpu().numpy(), want, precision, float(np.sum(ora.t.ptf)), "totals with clamped adaptation")
+    close(b.cpf.cpu().numpy(), ora.cpf, precision, ora.t.ptf, "capacities")
+    close(b.current_forces.cpu().numpy(), ora.current_forces, precision, ora.t.ptf, "forces")
+
+
+# --------------------------------------------------------------------------------------------------
+# Hill-type curves inside the step kernel
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_hill_epilogue_matches_the_reference_curves(cuda_device, precision):
+    specs = [MuscleSpec.standard(f) for f in (20.0, 32.0, 45.0, 32.0)]
+    agents, dt = 33, 0.02
+    rng = np.random.default_rng(2)
+    rest = rng.uniform(0.8, 1.2, (agents, 4))
+    cur = rest * rng.uniform(0.7, 1.5, (agents, 4))
+    prev = cur * rng.uniform(0.97, 1.03, (agents, 4))
+    act = rng.random((agents, 4))
+    a = MuscleBatch(specs, agents, cuda_device, precision)
+    ref = MuscleBatch(specs, agents, cuda_device, precision)
+    t = lambda v: torch.from_numpy(v).to(cuda_device, a.dtype)
+    out, fat = a.step_env(t(act), dt, hill=(t(rest), t(cur), t(prev)))
+    plain, fat0 = ref.step_env(t(act), dt)
+    # the reference's own functions on float64 NumPy inputs (bit-identical to pymuscle/hill_type.py, tests/golden/hill.npz)
+    gain = hill_type.contractile_element_force_length_curve(rest, cur) * \
+        hill_type.contractile_element_force_velocity_curve(rest, cur, prev, dt)
+    want = plain.double().cpu().numpy() * gain
+    rtol = 1e-9 if precision == "f64" else 2e-5
+    np.testing.assert_allclose(out.double().cpu().numpy(), want, rtol=rtol, atol=1e-300)
+    assert torch.equal(fat, fat0) and torch.equal(a.cpf, ref.cpf)
+
+
+def test_hill_golden_values_through_the_kernel(cuda_device):
+    """The curve samples of tests/golden/hill.npz (produced by the unmodified reference), one muscle per sample."""
+    g = golden("hill")
+    rest, cur, prev, dt = g["rest"], g["cur"], g["prev"], float(g["dt"])
+    m = rest.size
+    b = MuscleBatch(MuscleSpec.standard(), m, cuda_device, "f64")
+    ref = MuscleBatch(MuscleSpec.standard(), m, cuda_device, "f64")
+    t = lambda v: torch.from_numpy(np.ascontiguousarray(v, dtype=np.float64)).to(cuda_device).view(m, 1)
+    x = torch.full((m,), 0.7, dtype=torch.float64, device=cuda_device)
+    out, _ = b.step_env(x, dt, hill=(t(rest), t(cur), t(prev)))
+    plain, _ = ref.step_env(x, dt)
+    # atol: 1.8 - 1.8/(1 + e) cancels near 0 (see tests/test_hill_type.py)
+    np.testing.assert_allclose(out.cpu().numpy(), plain.cpu().numpy() * g["fl"] * g["fv"], rtol=1e-9, atol=1e-14)
+
+
+def test_env_adapter_uses_the_fused_hill_epilogue(cuda_device):
+    specs = [MuscleSpec.standard(f) for f in (20.0, 32.0)]
+    agents, dt = 16, 0.02
+    env = MuscleGroupEnv(specs, agents, cuda_device, "f64", rest_lengths=torch.tensor([1.0, 0.9]))
+    ora = [OracleMuscles.standard(20.0, m=agents), OracleMuscles.standard(32.0, m=agents)]
+    rng = np.random.default_rng(8)
+    rest = np.array([1.0, 0.9])
+    prev = None
+    launches0 = env.batch.launches
+    for step in range(6):
+        act = rng.random((agents, 2))
+        cur = rest * rng.uniform(0.85, 1.3, (agents, 2))
+        out, fat = env.step(torch.from_numpy(act), dt, lengths=torch.from_numpy(cur))
+        p = cur if prev is None else prev
+        gain = hill_type.contractile_element_force_length_curve(rest, cur) * \
+            hill_type.contractile_element_force_velocity_curve(rest, cur, p, dt)
+        want = np.stack([o.step(act[:, i], dt).total for i, o in enumerate(ora)], axis=1) * gain
+        np.testing.assert_allclose(out.cpu().numpy(), want, rtol=1e-9, atol=1e-14)
+        np.testing.assert_allclose(fat.cpu().numpy(), np.stack([o.peripheral_fatigue() for o in ora], axis=1),
+                                   rtol=1e-9, atol=1e-14)
+        prev = cur
+    assert env.batch.launches - launches0 == 6, "an env step must be exactly one launch"
+
+
+# --------------------------------------------------------------------------------------------------
+# fused fatigue readout
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_fused_fatigue_is_exactly_zero_at_rest_and_equals_the_standalone_kernel(cuda_device, precision):
+    specs = [MuscleSpec.standard(f) for f in (20.0, 32.0, 45.0)]
+    rows, dt = 21, 0.02
+    b = MuscleBatch(specs, rows, cuda_device, precision)
+    zero = torch.zeros(rows, 3, dtype=b.dtype, device=cuda_device)
+    _, fat = b.step_env(zero, dt)
+    assert torch.count_nonzero(fat) == 0, "a rested muscle must report fatigue exactly 0 (muscle.py:248-256)"
+    g = torch.Generator(device=cuda_device).manual_seed(1)
+    for _ in range(30):
+        _, fat = b.step_env(torch.rand(rows, 3, device=cuda_device, generator=g, dtype=b.dtype), dt)
+    alone = b.get_peripheral_fatigue()
+    torch.testing.assert_close(fat, alone, rtol=1e-12, atol=1e-15)     # both sum float64 capacities; order may differ
+    assert (fat > 0).all()
+
+
+# --------------------------------------------------------------------------------------------------
+# history capture
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_force_history_ring_matches_per_step_reads(cuda_device, precision):
+    spec, M, dt, every, window = MuscleSpec.standard(), 3, 0.02, 5, 40
+    b = MuscleBatch(spec, M, cuda_device, precision)
+    ref = MuscleBatch(spec, M, cuda_device, precision)
+    hist = ForceHistory(b, every=every, window=window, slots=2)
+    x = torch.tensor([0.6, 0.3, 0.9], dtype=b.dtype, device=cuda_device)
+    totals = []
+    for _ in range(5):                                                # 5 windows through a 2-slot ring: it wraps
+        totals.append(hist.advance(x, dt, steps=window))
+    rec = hist.collect()
+    want, want_tot = [], []
+    for k in range(5 * window):
+        want_tot.append(ref.step(x, dt))
+        if (k + 1) % every == 0:
+            want.append(ref.current_forces.double().cpu().numpy())
+    want = np.stack(want)
+    assert rec.shape == (5 * window // every, M, spec.n)
+    tol = dict(rtol=1e-9, atol=1e-12) if precision == "f64" else dict(rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(rec, want, **tol)
+    np.testing.assert_allclose(torch.cat(totals).double().cpu().numpy(), torch.stack(want_tot).double().cpu().numpy(), **tol)
+    assert hist.collect().shape[0] == 0
+
+
+# --------------------------------------------------------------------------------------------------
+# memory safety without the sanitizer: NaN guard bands around the state
+# --------------------------------------------------------------------------------------------------
+def _guarded(batch, pad=64):
+    """Move cpf / dur / forces of a batch into the middle of NaN-filled arenas (16-byte aligned views)."""
+    arenas = {}
+    for name in ("cpf", "dur"):
+        t = getattr(batch, name)
+        arena = torch.full((t.numel() + 2 * pad,), float("nan"), dtype=t.dtype, device=t.device)
+        view = arena[pad:pad + t.numel()].view_as(t)
+        view.copy_(t)
+        setattr(batch, name, view)
+        arenas[name] = arena
+    return arenas
+
+
+def _bands_intact(arenas, pad=64):
+    for name, a in arenas.items():
+        assert torch.isnan(a[:pad]).all() and torch.isnan(a[-pad:]).all(), f"{name}: a kernel wrote outside the array"
+
+
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+@pytest.mark.parametrize("shape", ["odd_uniform", "ragged_odd", "tiny", "wide"])
+def test_kernels_do_not_write_outside_their_state_arrays(cuda_device, precision, shape):
+    dt = 0.02
+    if shape == "odd_uniform":
+        spec, rows = MuscleSpec.potvin(33), 4099                      # odd row length, partial last chunk
+    elif shape == "ragged_odd":
+        spec, rows = [MuscleSpec.standard(f) for f in (9.0, 33.0, 21.0)], 2051
+    elif shape == "tiny":
+        spec, rows = MuscleSpec.potvin(2), 3
+    else:
+        spec, rows = MuscleSpec.standard(527.1), 259
+    b = MuscleBatch(spec, rows, cuda_device, precision)
+    arenas = _guarded(b)
+    ref = MuscleBatch(spec, rows, cuda_device, precision)
+    g = torch.Generator(device=cuda_device).manual_seed(0)
+    scale = 67.0 if shape in ("odd_uniform", "tiny") else 1.0
+    for _ in range(3):
+        x = scale * torch.rand(rows, b.S, device=cuda_device, generator=g, dtype=b.dtype)
+        got, want = b.step(x, dt), ref.step(x, dt)
+        assert torch.equal(got, want)
+        pu = scale * torch.rand(rows, b.L, device=cuda_device, generator=g, dtype=b.dtype)
+        assert torch.equal(b.step(pu, dt), ref.step(pu, dt))
+    out, fat = b.step_env(x, dt)
+    out2, fat2 = ref.step_env(x, dt)
+    assert torch.equal(out, out2) and torch.equal(fat, fat2)
+    if b.S == 1:
+        xs = scale * torch.rand(37, rows, device=cuda_device, generator=g, dtype=b.dtype)
+        assert torch.equal(b.step_many(xs, dt), ref.step_many(xs, dt))
+    torch.cuda.synchronize()
+    _bands_intact(arenas)
+    assert torch.equal(b.cpf, ref.cpf) and torch.equal(b.dur, ref.dur)
+    assert not torch.isnan(b.cpf).any() and not torch.isnan(b.dur).any()
+
+
+# --------------------------------------------------------------------------------------------------
+# small launches: the low-latency kernel against the streaming kernel
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_small_launch_kernel_matches_streaming_kernel(cuda_device, precision):
+    """Same batch stepped by two processes' worth of dispatch: MB_K1_SMALL=0 forces the streaming kernel.
+    (The knob is read once per process, so the comparison runs in a child.)"""
+    code = r'''
+import sys, torch, numpy as np
+sys.path.insert(0, %r)
+from pymuscle_b200 import MuscleBatch, MuscleSpec
+dev = torch.device("cuda:0")
+b = MuscleBatch([MuscleSpec.standard(f) for f in (20.0, 32.0, 45.0)], 40, dev, %r)
+g = torch.Generator(device=dev).manual_seed(4)
+outs = []
+for _ in range(25):
+    outs.append(b.step(torch.rand(40, 3, device=dev, generator=g, dtype=b.dtype), 0.02))
+np.save(sys.argv[1], torch.stack(outs).double().cpu().numpy())
+np.save(sys.argv[2], b.cpf.cpu().numpy())
+''' % (ROOT, precision)
+    import tempfile
+    res = {}
+    with tempfile.TemporaryDirectory() as d:
+        for tag, env in (("small", {}), ("stream", {"MB_K1_SMALL": "0"})):
+            p = [os.path.join(d, f"{tag}_{k}.npy") for k in ("tot", "cpf")]
+            subprocess.run([sys.executable, "-c", code] + p, check=True, env={**os.environ, **env}, timeout=300)
+            res[tag] = [np.load(q) for q in p]
+    rtol = 1e-12 if precision == "f64" else 1e-6                    # only the order of the per-muscle sum differs
+    np.testing.assert_allclose(res["small"][0], res["stream"][0], rtol=rtol, atol=1e-300)
+    np.testing.assert_array_equal(res["small"][1], res["stream"][1])
