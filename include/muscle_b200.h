@@ -253,7 +253,7 @@ typedef struct MbFusedArgs {
     void* forces_last_dev;
     void* const* peer_totals_dev;
     int32_t n_peers;
-    int32_t reserved;
+    int32_t max_segment_units;   /* S > 1: the longest muscle of a row (the host knows seg_off; the library only has the device copy) */
     int64_t peer_stride_k, peer_stride_pair;
 } MbFusedArgs;
 int mb_step_fused_ex(const MbConfig* cfg, const void* params_dev, const MbFusedArgs* args,

@@ -85,7 +85,7 @@ class MbFusedArgs(C.Structure):
         ("forces_last_dev", C.c_void_p),
         ("peer_totals_dev", C.POINTER(C.c_void_p)),
         ("n_peers", C.c_int32),
-        ("reserved", C.c_int32),
+        ("max_segment_units", C.c_int32),
         ("peer_stride_k", C.c_int64), ("peer_stride_pair", C.c_int64),
     ]
 

@@ -28,11 +28,12 @@ struct Knobs {
     int k1_w;            // MB_K1_W             streaming kernel: tile width cap (0 = default)
     int k1_bps;          // MB_K1_BPS           streaming kernel: cap on resident blocks per SM (0 = none)
     int k1_flat;         // MB_K1_FLAT          -1 auto, 0 never, 1 whenever eligible: flat-tiled kernel for ragged rows
-    int k1_small;        // MB_K1_SMALL         unit-steps per launch below which the low-latency kernel is used (-1 = default)
+    int k1_flat_group;   // MB_K1_FLAT_GROUP    flat-tiled kernel: target units per group of muscles (0 = 16 tiles)
     int fused_block;     // MB_FUSED_BLOCK=1    mb_step_fused: block kernel where it would pick a warp kernel
     int fused_no_bulk;   // MB_FUSED_NO_BULK=1  block kernel stages excitations with plain loads
     int fused_general;   // MB_FUSED_GENERAL=1  fused kernels keep every clamp of the reference
     int f64_block;       // MB_F64_BLOCK=1      FP64 mode: block kernel where it would pick the warp kernel
+    int fused_wide;      // MB_FUSED_WIDE=1     FP32 mode, n > 128: block-per-muscle kernel where it would pick the block kernel
 };
 const Knobs& knobs();
 

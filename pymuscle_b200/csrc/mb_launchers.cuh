@@ -3,6 +3,7 @@
 #include "mb_host.cuh"
 #include "mb_fused.cuh"      // K2Args
 #include "mb_stream.cuh"     // K1sArgs
+#include "mb_fused_wide.cuh"  // K2xArgs
 
 namespace mb {
 
@@ -13,12 +14,17 @@ namespace mb {
         void *totals, const K1sEpilogue &ep, double dt, cudaStream_t st
 int launch_k1s_f32(MB_K1S_PARAMS);
 int launch_k1s_f64(MB_K1S_PARAMS);
+// ---- k_flat_f32.cu / k_flat_f64.cu: the flat-tiled variant for rows of several muscles (k1_flat) ------
+int launch_k1f_f32(MB_K1S_PARAMS);
+int launch_k1f_f64(MB_K1S_PARAMS);
 
 // ---- k_fused_*.cu: the fused K-step kernels.  fib = MbFibers, cen = 0 / 1 / 2 (see CoreF32) ------
 int launch_k2_block_f32(const K2Args& a, const FusedGeom& g, int fib, int cen, bool forces, cudaStream_t st);
 int launch_k2_block_f64(const K2Args& a, const FusedGeom& g, int fib, int cen, bool forces, cudaStream_t st);
 int launch_k2w_f32(const K2Args& a, const FusedGeom& g, int fib, int cen, bool forces, cudaStream_t st);
 int launch_k2u_f32(const K2Args& a, const FusedGeom& g, int fib, int cen, bool forces, cudaStream_t st);
+int launch_k2w_f64(const K2Args& a, const FusedGeom& g, int fib, int cen, bool forces, cudaStream_t st);
+int launch_k2x_f32(const K2xArgs& xa, const FusedGeom& g, int fib, int cen, bool forces, cudaStream_t st);
 
 // launch with the opt-in to large dynamic shared memory (cheap; static bytes count towards the 48 KB default too)
 template <typename KernelT, typename ArgsT>

@@ -7,6 +7,9 @@
 //
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared ...
 #include "mb_launchers.cuh"
+#include "mb_fused_warp64.cuh"
+#include "mb_fused_wide.cuh"
+#include "mb_flat.cuh"
 #include "mb_fused_warp.cuh"     // tile constants of the warp kernels (geometry); nothing is instantiated here
 
 #include <cmath>
@@ -45,11 +48,12 @@ const Knobs& mb::knobs() {
         q.k1_w = env_int("MB_K1_W", 0);
         q.k1_bps = env_int("MB_K1_BPS", 0);
         q.k1_flat = env_int("MB_K1_FLAT", -1);
-        q.k1_small = env_int("MB_K1_SMALL", -1);
+        q.k1_flat_group = env_int("MB_K1_FLAT_GROUP", 0);
         q.fused_block = env_int("MB_FUSED_BLOCK", 0);
         q.fused_no_bulk = env_int("MB_FUSED_NO_BULK", 0);
         q.fused_general = env_int("MB_FUSED_GENERAL", 0);
         q.f64_block = env_int("MB_F64_BLOCK", 0);
+        q.fused_wide = env_int("MB_FUSED_WIDE", 0);
         return q;
     }();
     return k;
@@ -582,38 +586,6 @@ static int launch_k1(const MbConfig& c, const void* params, int64_t rows, int64_
     return MB_OK;
 }
 
-// Small launches: one row per block iteration (R = 1), every (row, muscle) its own work item.  The streaming
-// pipeline below needs ~20 us to fill and drain whatever the batch size; a batch of a few hundred muscles is
-// a few hundred thousand unit-steps and wants latency, not bytes in flight.
-template <typename T>
-static int launch_k1_small(const MbConfig& c, const void* params, int64_t rows, int64_t L, int32_t S,
-                           const int32_t* seg_off, const double* seg_div, const void* in, int32_t in_per_unit, double* cpf,
-                           double* dur, void* forces, void* totals, double dt, cudaStream_t st,
-                           const typename Vec<T>::S& sc) {
-    K1Args<T> a;
-    a.params = (const typename Vec<T>::P*)params;
-    a.param_stride = c.param_rows > 1 ? (int64_t)(sizeof(T) == 4 ? kGroupsF32 : kGroupsF64) * L : 0;
-    a.rows = rows; a.L = L; a.S = S; a.seg_off = seg_off; a.seg_div = seg_div;
-    a.stage = MB_STAGE_MUSCLE; a.in_per_unit = in_per_unit;
-    a.recovery = c.fibers_kind == MB_FIBERS_PYMUSCLE;
-    a.central = c.central_fatigue != 0;
-    a.peripheral = c.peripheral_fatigue != 0;
-    a.in = (const T*)in; a.cpf = cpf; a.dur = dur;
-    a.forces = (T*)forces; a.totals = (T*)totals; a.mask = nullptr; a.rates = nullptr;
-    a.dt = dt;
-    a.adk_d = -kLog2e / c.adaptation_time_constant;
-    a.max_dur = c.max_duration;
-    a.sc = sc;
-    const int64_t mean_n = (L + S - 1) / S;
-    int tx = (int)((mean_n + 31) / 32) * 32;
-    if (tx > 256) tx = 256;
-    if (tx < 32) tx = 32;
-    const int64_t items = rows * S;
-    k1_step<T, 1, 2><<<(unsigned)items, tx, 0, st>>>(a);
-    MB_CUDA_OK(cudaGetLastError());
-    return MB_OK;
-}
-
 // The streaming kernel covers the batched hot case: whole-muscle stage, one input per muscle or per unit,
 // no mask / rate outputs, 16-byte aligned state arrays (any row length).
 template <typename T>
@@ -639,10 +611,9 @@ static bool k1s_eligible(const MbConfig& c, int64_t L, int32_t stage, int32_t in
     return true;
 }
 
-// unit-steps per launch below which the low-latency kernel wins over the streaming pipeline (measured on B200)
-static int64_t small_launch_limit() {
-    const int v = knobs().k1_small;
-    return v >= 0 ? (int64_t)v : 400000;
+// Rows of several muscles with one input per muscle: the flat-tiled kernel (mb_flat.cuh)
+static bool use_flat(const MbConfig& c, int32_t S, int32_t in_per_unit) {
+    return S > 1 && S <= kFlatMaxS && !in_per_unit && c.param_rows <= 1 && knobs().k1_flat != 0;
 }
 
 extern "C" int mb_step(const MbConfig* cfg, const void* params_dev, int64_t rows, int64_t L, int32_t S,
@@ -661,22 +632,15 @@ extern "C" int mb_step(const MbConfig* cfg, const void* params_dev, int64_t rows
         return fail(MB_EINVAL, "mb_step: per-instance tables need a uniform batch with param_rows == rows");
     cudaStream_t st = (cudaStream_t)stream;
     const K1sEpilogue no_epilogue;
-    const bool small = stage == MB_STAGE_MUSCLE && !mask_dev && !rates_dev && rows * L <= small_launch_limit();
     if (cfg->precision == MB_F32) {
-        if (small)
-            return launch_k1_small<float>(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, in_dev, in_per_unit, cpf_dev,
-                                          dur_dev, forces_dev, totals_dev, step_size, st, scal_f(*cfg));
         if (k1s_eligible<float>(*cfg, L, stage, in_per_unit, in_dev, cpf_dev, dur_dev, mask_dev, rates_dev, forces_dev))
-            return launch_k1s_f32(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, in_dev, in_per_unit, cpf_dev,
+            return (use_flat(*cfg, S, in_per_unit) ? launch_k1f_f32 : launch_k1s_f32)(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, in_dev, in_per_unit, cpf_dev,
                                   dur_dev, forces_dev, totals_dev, no_epilogue, step_size, st);
         return launch_k1<float>(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, stage, in_dev, in_per_unit, cpf_dev,
                                 dur_dev, forces_dev, totals_dev, mask_dev, rates_dev, step_size, st, scal_f(*cfg));
     }
-    if (small)
-        return launch_k1_small<double>(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, in_dev, in_per_unit, cpf_dev,
-                                       dur_dev, forces_dev, totals_dev, step_size, st, scal_d(*cfg));
     if (k1s_eligible<double>(*cfg, L, stage, in_per_unit, in_dev, cpf_dev, dur_dev, mask_dev, rates_dev, forces_dev))
-        return launch_k1s_f64(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, in_dev, in_per_unit, cpf_dev,
+        return (use_flat(*cfg, S, in_per_unit) ? launch_k1f_f64 : launch_k1s_f64)(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, in_dev, in_per_unit, cpf_dev,
                               dur_dev, forces_dev, totals_dev, no_epilogue, step_size, st);
     return launch_k1<double>(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, stage, in_dev, in_per_unit, cpf_dev, dur_dev,
                              forces_dev, totals_dev, mask_dev, rates_dev, step_size, st, scal_d(*cfg));
@@ -699,13 +663,14 @@ static int step_env_impl(const MbConfig* cfg, const void* params_dev, int64_t ro
     if (cfg->precision == MB_F32) {
         if (!k1s_eligible<float>(*cfg, L, MB_STAGE_MUSCLE, 0, in_dev, cpf_dev, dur_dev, nullptr, nullptr, forces_dev, ep.fatigue))
             return fail(MB_EUNSUPPORTED, "mb_step_env needs 16-byte aligned state arrays and peripheral fatigue on");
-        return launch_k1s_f32(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, in_dev, 0, cpf_dev, dur_dev,
-                              forces_dev, totals_dev, ep, step_size, st);
+        return (use_flat(*cfg, S, 0) ? launch_k1f_f32 : launch_k1s_f32)(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev,
+                                                                        in_dev, 0, cpf_dev, dur_dev, forces_dev, totals_dev,
+                                                                        ep, step_size, st);
     }
     if (!k1s_eligible<double>(*cfg, L, MB_STAGE_MUSCLE, 0, in_dev, cpf_dev, dur_dev, nullptr, nullptr, forces_dev, ep.fatigue))
         return fail(MB_EUNSUPPORTED, "mb_step_env needs 16-byte aligned state arrays and peripheral fatigue on");
-    return launch_k1s_f64(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, in_dev, 0, cpf_dev, dur_dev,
-                          forces_dev, totals_dev, ep, step_size, st);
+    return (use_flat(*cfg, S, 0) ? launch_k1f_f64 : launch_k1s_f64)(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, in_dev,
+                                                                    0, cpf_dev, dur_dev, forces_dev, totals_dev, ep, step_size, st);
 }
 
 extern "C" int mb_step_env(const MbConfig* cfg, const void* params_dev, int64_t rows, int64_t L, int32_t S,
@@ -754,6 +719,7 @@ extern "C" int mb_peripheral_fatigue(const MbConfig* cfg, int64_t rows, int64_t 
 
 // ---- fused geometry ---------------------------------------------------------------------
 static const int kFusedMaxUnits = 480;     // threads per block <= 480 (15 warps), 2 blocks per SM in FP32 mode
+static const int kWideMaxUnits = 4096;     // block-per-muscle kernel: 512 threads x 4 pairs of units
 
 static int fused_geometry(const MbConfig& c, int64_t M, int32_t n, int32_t K, int32_t upt, FusedGeom* g,
                           bool forces = false) {
@@ -772,6 +738,16 @@ static int fused_geometry(const MbConfig& c, int64_t M, int32_t n, int32_t K, in
         g->ns = n; g->npg = 0; g->ptp = 0;
         g->threads = kWarpsPerBlock * 32;
         g->smem = kWarpsPerBlock * (kWTile * kUPitch + 2 * kWTile) * (int)sizeof(float);
+        g->blocks = (M + g->G - 1) / g->G;
+        return MB_OK;
+    }
+    if (!f32 && upt == 0 && n >= 12 && n <= 128 && c.firing_gain == 1.0 && !knobs().f64_block) {
+        // FP64 mode, 12..128 units: one warp per muscle, no cross-warp reduction; every muscle may have its own table
+        g->kernel = FK_WARP_F64;
+        g->U = 1; g->q = kW64Warps; g->G = kW64Warps; g->Gp = g->G; g->T = kW64Tile;
+        g->ns = n; g->npg = 0; g->ptp = 0;
+        g->threads = kW64Warps * 32;
+        g->smem = kW64Warps * (kW64Tile * kW64Pitch + 2 * kW64Tile) * (int)sizeof(double);
         g->blocks = (M + g->G - 1) / g->G;
         return MB_OK;
     }
@@ -840,7 +816,7 @@ extern "C" int mb_step_fused_ex(const MbConfig* cfg, const void* params_dev, con
     if (cfg->central_fatigue && !w->dur_dev) return fail(MB_EINVAL, "mb_step_fused: dur is NULL");
     if (w->rows <= 0 || w->L <= 0 || w->K <= 0) return fail(MB_EINVAL, "mb_step_fused: rows, L and K must be positive");
     const int32_t S = w->S > 0 ? w->S : 1;
-    if (S > 1) return fail(MB_EUNSUPPORTED, "mb_step_fused: rows of several muscles are not covered by a fused kernel");
+    if (S > 1 && !w->seg_off_dev) return fail(MB_EINVAL, "mb_step_fused: seg_off required when S > 1");
     if (w->L > INT32_MAX) return fail(MB_EINVAL, "mb_step_fused: L too large");
     const int64_t M = w->rows * S;
     const int32_t n = (int32_t)w->L, K = w->K;
@@ -848,8 +824,27 @@ extern "C" int mb_step_fused_ex(const MbConfig* cfg, const void* params_dev, con
     if (w->forces_every < 0 || (w->forces_every > 0 && !w->forces_dec_dev)) return fail(MB_EINVAL, "mb_step_fused: forces_every without buffer");
     if (w->exc_stride_k != 0 && w->exc_stride_k < M) return fail(MB_EINVAL, "mb_step_fused: exc_stride_k < M");
     if (w->totals_dev && w->totals_stride_k < M) return fail(MB_EINVAL, "mb_step_fused: totals_stride_k < M");
+    // ---- which kernel: rows of several muscles and muscles wider than the block kernel's 480 units run one block
+    // per muscle (FP32 mode; up to 4,096 units per muscle)
+    const int32_t maxn = S > 1 ? (w->max_segment_units > 0 ? w->max_segment_units : n) : n;
+    const bool wide = cfg->precision == MB_F32 && maxn >= 2 && maxn <= kWideMaxUnits &&
+                      (S > 1 || n > kFusedMaxUnits || (knobs().fused_wide && n > 128));
+    if (!wide && S > 1)
+        return fail(MB_EUNSUPPORTED, "mb_step_fused: rows of several muscles need FP32 mode and muscles of at most %d units",
+                    kWideMaxUnits);
     FusedGeom g;
-    if (int rc = fused_geometry(*cfg, M, n, K, w->units_per_thread, &g, w->forces_every > 0)) return rc;
+    if (wide) {
+        if (cfg->param_rows > 1 && (S != 1 || cfg->param_rows != M)) return fail(MB_EINVAL, "per-instance tables need a uniform batch with param_rows == M");
+        g.kernel = FK_WIDE;
+        g.threads = maxn <= 2048 ? 256 : 512;
+        g.U = (maxn + 2 * g.threads - 1) / (2 * g.threads);  // pairs per thread
+        const int nw = g.threads / 32;
+        g.q = 1; g.G = 1; g.Gp = 1; g.T = kXTile; g.ns = maxn; g.npg = 0; g.ptp = 0;
+        g.smem = (nw * (kXTile * kXPitch + 2 * kXTile) + 2 * kXTile * (nw + 1)) * (int)sizeof(float);
+        g.blocks = M;
+    } else if (int rc = fused_geometry(*cfg, M, n, K, w->units_per_thread, &g, w->forces_every > 0)) {
+        return rc;
+    }
     const bool f32 = cfg->precision == MB_F32;
     const int esz = f32 ? 4 : 8;
 
@@ -904,12 +899,21 @@ extern "C" int mb_step_fused_ex(const MbConfig* cfg, const void* params_dev, con
     const int fib = cfg->fibers_kind;
     const bool forces = w->forces_every > 0;
     cudaStream_t st = (cudaStream_t)stream;
+    if (g.kernel == FK_WIDE) {
+        K2xArgs xa;
+        xa.k = a;
+        xa.L = w->L; xa.total_units = w->rows * w->L; xa.S = S;
+        xa.seg_off = S > 1 ? w->seg_off_dev : nullptr;
+        xa.seg_div = S > 1 ? w->seg_div_dev : nullptr;
+        return launch_k2x_f32(xa, g, fib, cen, forces, st);
+    }
     if (g.kernel == FK_WARP_UNITS) return launch_k2u_f32(a, g, fib, cen, forces, st);
     if (g.kernel == FK_WARP_PAIR) return launch_k2w_f32(a, g, fib, cen, forces, st);
     if (f32) return launch_k2_block_f32(a, g, fib, cen, forces, st);
     // FP64: the fast path additionally needs the sigmoid's exponent bounded (no clamp in exp_neg_fast);
     // without central fatigue the clamp is kept (CENTRAL == 0 instantiates it)
     if (cen == 1 && !(cfg->table_props & MB_PROP_EXP_BOUNDED)) cen = 2;
+    if (g.kernel == FK_WARP_F64) return launch_k2w_f64(a, g, fib, cen, forces, st);
     return launch_k2_block_f64(a, g, fib, cen, forces, st);
 }
 

@@ -153,9 +153,13 @@ def test_fused_geometry_for_the_headline_config():
                                     C.byref(blocks), C.byref(smem)))
     assert thr.value == 480 and mpb.value == 16 and blocks.value == 4096
     assert smem.value <= 110 * 1024
-    # FP64 mode: 4 instances per thread, one block per SM
+    # FP64 mode: one warp per muscle, 8 muscles per block, two blocks per SM
     cfg64 = pack_row([MuscleSpec.potvin(120)], nat.MB_F64).cfg
     nat.check(lib.mb_fused_geometry(C.byref(cfg64), 32768, 120, 1000, 0, C.byref(mpb), C.byref(thr),
+                                    C.byref(blocks), C.byref(smem)))
+    assert thr.value == 256 and mpb.value == 8 and blocks.value == 4096 and smem.value <= 110 * 1024
+    # ... explicit units_per_thread: the FP64 block kernel, 4 instances per thread, one block per SM
+    nat.check(lib.mb_fused_geometry(C.byref(cfg64), 32768, 120, 1000, 4, C.byref(mpb), C.byref(thr),
                                     C.byref(blocks), C.byref(smem)))
     assert thr.value == 480 and mpb.value == 16 and smem.value <= 220 * 1024
 
