@@ -148,7 +148,7 @@ int mb_step(const MbConfig* cfg, const void* params_dev,
  * factors of pymuscle/hill_type.py:15-66).
  *   in_dev        [rows, S] one excitation per muscle
  *   out_gain_dev  [rows, S] totals are multiplied by it; may be NULL
- *   fatigue_dev   [rows, S] float64, 1 - sum(new capacities)/output divisor; may be NULL
+ *   fatigue_dev   [rows, S] float64, sum(peak - new capacity)/output divisor (see mb_peripheral_fatigue); may be NULL
  * Returns MB_EUNSUPPORTED for layouts the streaming kernel does not cover (state arrays not
  * 16-byte aligned, peripheral fatigue off); the caller then uses mb_step + mb_peripheral_fatigue. */
 int mb_step_env(const MbConfig* cfg, const void* params_dev,
@@ -264,9 +264,11 @@ int mb_step_fused_ex(const MbConfig* cfg, const void* params_dev, const MbFusedA
 int mb_fused_geometry(const MbConfig* cfg, int64_t M, int32_t n, int32_t K, int32_t units_per_thread,
                       int32_t* muscles_per_block, int32_t* threads, int64_t* blocks, int32_t* smem_bytes);
 
-/* ---- per-muscle capacity sums: StandardMuscle.get_peripheral_fatigue (muscle.py:248-256)
- * fatigue[rows, S] = 1 - sum(cpf) / output_divisor, as float64. */
-int mb_peripheral_fatigue(const MbConfig* cfg, int64_t rows, int64_t L, int32_t S,
+/* ---- per-muscle lost capacity: StandardMuscle.get_peripheral_fatigue (muscle.py:248-256)
+ * fatigue[rows, S] = sum(peak - cpf) / output_divisor, as float64 -- the reference's 1 - sum(cpf)/max_arb_output
+ * with max_arb_output = sum(peak) (muscle.py:187) taken inside the sum: equal up to rounding, but exactly 0 for a rested
+ * muscle whatever the order of the parallel sum, and never negative.  mb_step_env's fused readout is the same quantity. */
+int mb_peripheral_fatigue(const MbConfig* cfg, const void* params_dev, int64_t rows, int64_t L, int32_t S,
                           const int32_t* seg_off_dev, const double* seg_div_dev, const double* cpf_dev,
                           double* fatigue_dev, void* stream);
 

@@ -129,7 +129,7 @@ def _declare(lib):
     lib.mb_fused_geometry.argtypes = [cfgp, i64, i32, i32, i32, C.POINTER(i32), C.POINTER(i32),
                                       C.POINTER(i64), C.POINTER(i32)]
     lib.mb_peripheral_fatigue.restype = C.c_int
-    lib.mb_peripheral_fatigue.argtypes = [cfgp, i64, i64, i32, vp, vp, vp, vp, vp]
+    lib.mb_peripheral_fatigue.argtypes = [cfgp, vp, i64, i64, i32, vp, vp, vp, vp, vp]
     lib.mb_step_env_hill.restype = C.c_int
     lib.mb_step_env_hill.argtypes = [cfgp, vp, i64, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(MbHill), dbl, vp]
     lib.mb_step_fused_ex.restype = C.c_int

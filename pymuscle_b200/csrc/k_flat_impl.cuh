@@ -60,7 +60,7 @@ static int launch_k1f(MB_K1S_PARAMS, const typename StreamTraits<T>::S& sc) {
     const int threads = W + 32, ncw = W / 32;
     const int stage_bytes = kStreamRows * (W + 2) * 8 * (central ? 2 : 1) + StreamTraits<T>::G * W * 16;
     const int smem = 128 + NS * stage_bytes + NS * kStreamRows * kFlatMaxSegs * (int)sizeof(T) +
-                     2 * ncw * kFlatMaxSegs * kStreamRows * ((fatigue ? 8 : 0) + (int)sizeof(T)) + 8 +
+                     2 * ncw * kFlatMaxSegs * kStreamRows * (fatigue ? 2 : 1) * (int)sizeof(T) + 8 +
                      S * 8 + (S + 1) * 4 + (kFlatMaxGroups + 1) * 4 + 16;
     const int64_t max_items = ((rows + kStreamRows - 1) / kStreamRows) * (int64_t)S;   // (an upper bound: groups <= muscles)
 #define MB_K1F_F(C_, R_, F_) (fatigue ? launch_k1f_variant<T, C_, R_, F_, true>(fa, threads, smem, max_items, st) \

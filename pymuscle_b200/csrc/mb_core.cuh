@@ -155,27 +155,44 @@ static __constant__ double kExp2Tab[32] = {
     0x1.ae89f995ad3adp+0, 0x1.b7f76f2fb5e47p+0, 0x1.c199bdd85529cp+0, 0x1.cb720dcef9069p+0,
     0x1.d5818dcfba487p+0, 0x1.dfc97337b9b5fp+0, 0x1.ea4afa2a490dap+0, 0x1.f50765b6e4540p+0};
 
-// exp(x) for -700 <= x <= 0 in about a dozen FP64 instructions (the library exp needs ~2.5x
-// as many): x = n*ln2/32 + r, |r| <= ln2/64, exp(x) = 2^(n>>5) * 2^((n&31)/32) * P5(r).
-// Relative error < 1e-14 (truncation r^6/720 = 2e-15, two-step reduction); the FP64 mode's
-// bar is 1e-9.  (A degree-4 polynomial would still meet the bar but measured no faster: the
-// FP64 kernels are bound by latency and issue, not by the FP64 instruction count.)  `tab` is a shared-memory copy of kExp2Tab (divergent index).
+// exp(x) for -700 <= x <= 0 in ten FP64 instructions (the library exp needs ~3x as many):
+// x = n*ln2/32 + r, |r| <= ln2/64, exp(x) = 2^(n>>5) * 2^((n&31)/32) * P4(r).
+//   * reduction: ONE fma with ln2/32 rounded to double -- the product is exact inside the fma, so the only error
+//     is the constant's 2^-53 relative error: |x| * 1.1e-16 <= 8e-14 absolute in r, i.e. relative in exp(x);
+//   * P4 = degree-4 Taylor: truncation r^5/120 <= 1.3e-12.
+// Relative error < 2e-12 against the FP64 mode's 1e-9 bar (errors in the normalised force enter the capacity
+// decrement linearly, they are not amplified over the steps).  `tab` is a shared-memory copy of kExp2Tab
+// (divergent index).
+// The four constants that are not 32-bit immediates.  Written as literals the compiler rebuilds each of them with two
+// moves per use (8 issue slots per exponential); a kernel that passes them in through its argument struct (constant
+// bank -> uniform registers, loaded once) gets them for free.
+struct ExpConsts {
+    double k32_ln2;      // 32 / ln 2
+    double nln2_32;      // -(ln 2) / 32
+    double c24, c6;      // 1/24, 1/6
+};
+__host__ __device__ __forceinline__ ExpConsts exp_consts() {
+    return ExpConsts{0x1.71547652b82fep+5, -0x1.62e42fefa39efp-6, 1.0 / 24.0, 1.0 / 6.0};
+}
+
 template <bool CLAMP>
-__device__ __forceinline__ double exp_neg_fast(double x, const double* tab) {
+__device__ __forceinline__ double exp_neg_fast(double x, const double* tab, const ExpConsts& k) {
     if (CLAMP) x = fmax(x, -700.0);                                     // (the launcher proves it redundant for most tables)
     const double kMagic = 6755399441055744.0;                          // 1.5 * 2^52: round to integer
-    const double t = fma(x, 0x1.71547652b82fep+5, kMagic);              // x * 32/ln2
+    const double t = fma(x, k.k32_ln2, kMagic);
     const int n = __double2loint(t);
     const double nf = t - kMagic;
-    double r = fma(nf, -0x1.62e42f8000000p-6, x);                       // ln2/32, upper 25 bits (exact product)
-    r = fma(nf, -0x1.be8e7bcd5e4f2p-32, r);                             // ln2/32, remainder
-    double p = fma(r, 1.0 / 120.0, 1.0 / 24.0);
-    p = fma(p, r, 1.0 / 6.0);
+    const double r = fma(nf, k.nln2_32, x);
+    double p = fma(r, k.c24, k.c6);
     p = fma(p, r, 0.5);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
     const double s = tab[n & 31] * p;
     return __hiloint2double(__double2hiint(s) + ((n >> 5) << 20), __double2loint(s));
+}
+template <bool CLAMP>
+__device__ __forceinline__ double exp_neg_fast(double x, const double* tab) {
+    return exp_neg_fast<CLAMP>(x, tab, exp_consts());
 }
 
 // fibers_force with the fast exponential (fused kernel)

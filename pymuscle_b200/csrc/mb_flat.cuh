@@ -56,8 +56,8 @@ k1_flat(const K1fArgs<T> fa) {
     P* par_s = (P*)(CENTRAL ? dur_s + (size_t)NS * R * rowp : dur_s);     // [NS][G][W]
     T* xin_s = (T*)(par_s + (size_t)NS * G * W);          // [NS][R][NSG] the item's per-muscle inputs
     const int ncons = blockDim.x - 32, ncw = ncons >> 5;
-    double* accc = (double*)(xin_s + (size_t)NS * R * NSG);   // [2][ncw][NSG][R] capacity sums (FATIGUE)
-    T* accf = (T*)(accc + (FATIGUE ? 2 * ncw * NSG * R : 0));  // [2][ncw][NSG][R] force sums
+    T* accc = xin_s + (size_t)NS * R * NSG;               // [2][ncw][NSG][R] capacity deficits (FATIGUE)
+    T* accf = accc + (FATIGUE ? 2 * ncw * NSG * R : 0);   // [2][ncw][NSG][R] force sums
     double* segdiv_s = (double*)(accf + 2 * ncw * NSG * R + ((2 * ncw * NSG * R) & 1));   // [S] (8-byte aligned)
     int32_t* segoff_s = (int32_t*)(segdiv_s + S);         // [S + 1]
     int32_t* grp_s = segoff_s + S + 1;                    // [ng + 1] first muscle of every group
@@ -174,14 +174,13 @@ k1_flat(const K1fArgs<T> fa) {
         const int nrows = (int)min((int64_t)R, a.rows - r0);
         const int buf = item_no & 1;
         T* af = accf + (size_t)(buf * ncw + warp) * NSG * R;            // this warp's slots [NSG][R]
-        double* ac = accc + (size_t)(buf * ncw + warp) * NSG * R;
+        T* ac = accc + (size_t)(buf * ncw + warp) * NSG * R;
         for (int i = lane; i < NSG * R; i += 32) {
             af[i] = T(0);
-            if (FATIGUE) ac[i] = 0.0;
+            if (FATIGUE) ac[i] = T(0);
         }
         __syncwarp();
-        T partial[R];
-        double csum[R];
+        T partial[R], csum[R];                            // forces; lost capacity sum(peak - new capacity)
 #pragma unroll
         for (int r = 0; r < R; ++r) { partial[r] = 0; csum[r] = 0; }
         int wseg = -1;                                    // the muscle this warp's registers are accumulating (-1: none)
@@ -194,10 +193,10 @@ k1_flat(const K1fArgs<T> fa) {
             const T wf = warp_sum_rows8(t, lane);
             if ((lane & 3) == 0) af[sl * R + rr] += wf;
             if (FATIGUE) {
-                double tc[R];
+                T tc[R];
 #pragma unroll
-                for (int r = 0; r < R; ++r) tc[r] = mine ? csum[r] : 0.0;
-                const double wc = warp_sum_rows8(tc, lane);
+                for (int r = 0; r < R; ++r) tc[r] = mine ? csum[r] : T(0);
+                const T wc = warp_sum_rows8(tc, lane);
                 if ((lane & 3) == 0) ac[sl * R + rr] += wc;
             }
         };
@@ -222,7 +221,7 @@ k1_flat(const K1fArgs<T> fa) {
             if (active) {
                 const P* pst = par_s + (size_t)(s * G) * W;
                 const auto p = load_unit_staged(pst, W, tid);
-                const double fatdt = (double)p.fat * a.dt, rdidt = (double)p.rdi * a.dt;
+                const auto fatdt = rate_dt(p.fat, a.dt), rdidt = rate_dt(p.rdi, a.dt);   // float in FP32 mode, double in FP64 mode
                 const double ptf = unit_peak(p);
                 const double* cs = cpf_s + (s * R) * rowp + tid;
                 const double* ds = dur_s + (s * R) * rowp + tid;
@@ -242,7 +241,7 @@ k1_flat(const K1fArgs<T> fa) {
                         *cp = cn;
                         if (CENTRAL) *dp = dn;
                         partial[r] += F;
-                        if (FATIGUE) csum[r] += cn;
+                        if (FATIGUE) csum[r] += (T)(ptf - cn);
                     }
                     if (FORCES) fp += a.L;
                     cp += a.L;
@@ -277,10 +276,10 @@ k1_flat(const K1fArgs<T> fa) {
                 a.totals[mu] = sum;
             }
             if (FATIGUE) {
-                const double* q0 = accc + (size_t)(buf * ncw) * NSG * R + sl * R + r;
-                double cs = q0[0];
+                const T* q0 = accc + (size_t)(buf * ncw) * NSG * R + sl * R + r;
+                T cs = q0[0];
                 for (int w = 1; w < ncw; ++w) cs += q0[(size_t)w * NSG * R];
-                a.fatigue[mu] = 1.0 - cs / (seg_div ? seg_div[sg] : a.fat_div);
+                a.fatigue[mu] = (double)cs / (seg_div ? seg_div[sg] : a.fat_div);     // lost capacity / max_arb_output (see mb_stream.cuh)
             }
         }
         ++item_no;

@@ -73,6 +73,7 @@ struct K2Args {
     float decay, dm1;            // (float)decay_d and decay - 1 (exact in float)
     ScalF sf;
     ScalD sd;
+    ExpConsts ec;                // exp_neg_fast's constants (FP64 mode)
 };
 
 // U-wide vector of T in shared memory (one LDS/STS of 4*U or 8*U bytes)

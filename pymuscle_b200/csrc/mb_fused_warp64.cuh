@@ -15,15 +15,23 @@
 //
 // Arithmetic: CoreF64's (mb_fused.cuh) -- reference operation order for the recruitment mask, G = 1 -
 // exp(-dur/tau) by recurrence with an integer on-step counter (fast path) or the reference's literal
-// clamps (general path), the table-based exp_neg_fast for the force sigmoid.  The UPL chains advance in
+// clamps (general path), the table-based exp_neg_fast for the force sigmoid.  The chains of a thread advance in
 // three phases (rates, exponentials, forces + fatigue) with ONE branch around the exponentials, so the
-// scheduler can interleave them.
+// scheduler can interleave them; groups of 32 units without a recruited unit are skipped (see do_step).
 #pragma once
 #include "mb_fused.cuh"
 #include <type_traits>
 
 namespace mb {
 
+#ifndef MB_W64_SKIP
+#define MB_W64_SKIP 1              // 0: every group every step; 1: skip muscles entirely at rest; 2: skip every group at rest
+                                   // (measured: 1 wins -- the per-step switch of 2 costs more than the groups it skips)
+#endif
+#ifndef MB_W64_UNROLL
+#define MB_W64_UNROLL 2
+#endif
+constexpr int kW64Unroll = MB_W64_UNROLL;   // unroll factor of the step loop
 constexpr int kW64Tile = 32;       // steps per tile
 constexpr int kW64Pitch = 33;      // row pitch of the force tile in doubles (odd => conflict free)
 constexpr int kW64Warps = 8;       // warps (muscles) per block
@@ -99,73 +107,123 @@ k2w_f64(const K2Args a) {
         auto do_step = [&](int s, auto last_tag) {
             constexpr bool LAST = decltype(last_tag)::value;
             const double e = __dmul_rn(es[s], sc.input_scale);                    // muscle.py:275, once per muscle-step
-            double x[UPL], ex[UPL];
+            double r0[UPL];
             bool on[UPL];
-            bool need = false;
+            unsigned gmask = 0;
 #pragma unroll
             for (int i = 0; i < UPL; ++i) {
-                const double r0 = __dadd_rn(__dsub_rn(e, thr[i]), sc.min_rate);  // pool:169-170
-                on[i] = !(r0 < sc.min_rate);                                      // pool:171
-                double r, fr;
-                if (CENTRAL == 1) {
-                    r = fmin(r0, peak[i]);                                        // pool:173 (gain == 1), :176-177
-                    const double q = fma(r, phir[i], -phir6[i]);                  // pool:231-232
-                    fr = on[i] ? fma(-q, G[i], r) : 0.0;                          // pool:217-221, :121 (dur BEFORE the update)
-                    if (on[i]) {                                                  // pool:196-197
-                        cnt[i] += 1;
-                        G[i] = fma(G[i], decay, omd);
-                    }
-                } else {
-                    r = (on[i] ? r0 : 0.0);                                       // pool:172, :173 (gain == 1)
-                    r = (r > peak[i]) ? peak[i] : r;                              // pool:176-177
-                    fr = r;
-                    if (CENTRAL == 2) {
-                        const double q = fma(r, phir[i], -phir6[i]);
-                        const double ad = q * G[i];                               // pool:217-219 (dur BEFORE the update)
-                        fr = r - ((ad < 0.0) ? 0.0 : ad);                         // pool:221, :121
-                        if (r > 0.0) {                                            // pool:196-197
-                            const double dn = dur[i] + dt;
-                            const bool clamp = dn > max_dur;                      // pool:202-203
-                            dur[i] = clamp ? max_dur : dn;
-                            G[i] = clamp ? Gmax : fma(G[i], decay, omd);
-                        }
-                    }
-                }
-                x[i] = fma(cpf[i], -ctB2[i], ctA2[i]) * fr;                       // cbrt(2) * (fibers:220 with the fatigued contraction time)
-                need |= x[i] > xlin;
+                r0[i] = __dadd_rn(__dsub_rn(e, thr[i]), sc.min_rate);            // pool:169-170
+                on[i] = !(r0[i] < sc.min_rate);                                   // pool:171
+                gmask |= (__any_sync(0xffffffffu, on[i]) ? 1u : 0u) << i;
             }
-            if (need) {
-#pragma unroll
-                for (int i = 0; i < UPL; ++i) ex[i] = exp_neg_fast<CENTRAL != 1>(-(x[i] * x[i]) * x[i], exp2_tab);   // exp(-2 x^3)
-            } else {
-#pragma unroll
-                for (int i = 0; i < UPL; ++i) ex[i] = 1.0;
-            }
-            double fsum = 0.0;
+            // A unit that is not recruited produces no force and (Potvin fibers) keeps its state, so a whole GROUP of 32
+            // units without a recruited one costs nothing beyond the three operations above.  Thresholds grow with the
+            // unit index, so the recruited groups are the leading ones: `kon` = groups to advance (warp-uniform; any
+            // table order is handled, a hole just computes a group of zeros).  One branch per step selects straight-
+            // line code for kon groups, inside which the chains interleave as before.
+#if MB_W64_SKIP == 2
+            const int kon = 32 - __clz(gmask);
+#elif MB_W64_SKIP == 1
+            const int kon = gmask ? UPL : 0;                                     // only a muscle entirely at rest is skipped
+#else
+            const int kon = UPL;
+#endif
             bool write_now = false;
             if (FORCES) write_now = ((k0 + s + 1) % a.forces_every) == 0;
-#pragma unroll
-            for (int i = 0; i < UPL; ++i) {
-                const double nf = (x[i] <= xlin) ? x[i] * c25s : 1.0 - ex[i];    // fibers:233-246
-                const double F = nf * cpf[i];                                     // fibers:258 (capacity BEFORE the update)
-                cpf[i] = fatigue_update<FIB == MB_FIBERS_PYMUSCLE>(cpf[i], nf, fatdt[i], rdidt[i], ptf[i]);
-                fsum = (i == 0) ? F : fsum + F;
+            auto emit = [&](int i, double F, bool oni) {                        // per-unit outputs of the FORCES / LAST variants
                 if (FORCES || LAST) {
                     const int u = lane + 32 * i;
                     if (u < n) {
                         if (FORCES && write_now) {
                             const int64_t idx = (int64_t)((k0 + s) / a.forces_every) * a.M * n + m * n + u;
                             ((double*)a.forces_dec)[idx] = F;
-                            if (a.mask_dec) a.mask_dec[idx] = on[i] ? 1 : 0;
+                            if (a.mask_dec) a.mask_dec[idx] = oni ? 1 : 0;
                         }
                         if (LAST) ((double*)a.forces_last)[m * n + u] = F;
                     }
                 }
+            };
+            auto body = [&](auto kon_tag) {
+                constexpr int KON = decltype(kon_tag)::value;
+                double x[KON > 0 ? KON : 1], nf[KON > 0 ? KON : 1];
+                bool lin[KON > 0 ? KON : 1];
+                bool all_lin = true;
+#pragma unroll
+                for (int i = 0; i < KON; ++i) {
+                    double fr;
+                    if (CENTRAL == 1) {
+                        // (plain compare + select: fmin() drags NaN handling along -- DSETP.MIN + SEL + FSEL + LOP3 + moves)
+                        const double r = (r0[i] > peak[i]) ? peak[i] : r0[i];     // pool:173 (gain == 1), :176-177
+                        const double q = fma(r, phir[i], -phir6[i]);              // pool:231-232
+                        const double fa = fma(-q, G[i], r);                       // pool:217-221, :121 (dur BEFORE the update)
+                        fr = on[i] ? fa : 0.0;
+                        // on-step counter and G <- G * decay + (1 - decay) of a firing unit (pool:196-197), branch-free:
+                        // written as `if (on) {...}` the compiler emits a divergent branch per unit, which serialises the chains
+                        const double Gn = fma(G[i], decay, omd);
+                        G[i] = on[i] ? Gn : G[i];
+                        asm("{\n\t.reg .pred p;\n\tsetp.geu.f64 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}"   // one predicated add
+                            : "+r"(cnt[i]) : "d"(r0[i]), "d"(sc.min_rate));
+                    } else {
+                        double r = (on[i] ? r0[i] : 0.0);                         // pool:172, :173 (gain == 1)
+                        r = (r > peak[i]) ? peak[i] : r;                          // pool:176-177
+                        fr = r;
+                        if (CENTRAL == 2) {
+                            const double q = fma(r, phir[i], -phir6[i]);
+                            const double ad = q * G[i];                           // pool:217-219 (dur BEFORE the update)
+                            fr = r - ((ad < 0.0) ? 0.0 : ad);                     // pool:221, :121
+                            if (r > 0.0) {                                        // pool:196-197
+                                const double dn = dur[i] + dt;
+                                const bool clamp = dn > max_dur;                  // pool:202-203
+                                dur[i] = clamp ? max_dur : dn;
+                                G[i] = clamp ? Gmax : fma(G[i], decay, omd);
+                            }
+                        }
+                    }
+                    x[i] = fma(cpf[i], -ctB2[i], ctA2[i]) * fr;                   // cbrt(2) * (fibers:220 with the fatigued contraction time)
+                    lin[i] = x[i] <= xlin;                                        // fibers:233-236
+                    all_lin = all_lin && lin[i];
+                }
+                if (!all_lin) {                                                   // one branch for the group of chains (see header)
+                    double ex[KON > 0 ? KON : 1];
+#pragma unroll
+                    for (int i = 0; i < KON; ++i) {
+                        ex[i] = exp_neg_fast<CENTRAL != 1>(-(x[i] * x[i]) * x[i], exp2_tab, a.ec);   // exp(-2 x^3)
+                        // (opaque use: otherwise the compiler sinks each exponential into a divergent per-unit branch
+                        //  `lin ? line : sigmoid`, and the four Horner chains run one after the other)
+                        asm volatile("" : "+d"(ex[i]));
+                    }
+#pragma unroll
+                    for (int i = 0; i < KON; ++i) nf[i] = lin[i] ? x[i] * c25s : 1.0 - ex[i];   // fibers:233-246
+                } else {
+#pragma unroll
+                    for (int i = 0; i < KON; ++i) nf[i] = x[i] * c25s;
+                }
+                double fsum = 0.0;
+#pragma unroll
+                for (int i = 0; i < KON; ++i) {
+                    const double F = nf[i] * cpf[i];                              // fibers:258 (capacity BEFORE the update)
+                    cpf[i] = fatigue_update<FIB == MB_FIBERS_PYMUSCLE>(cpf[i], nf[i], fatdt[i], rdidt[i], ptf[i]);
+                    fsum = (i == 0) ? F : fsum + F;
+                    emit(i, F, on[i]);
+                }
+#pragma unroll
+                for (int i = KON; i < UPL; ++i) {                                 // groups at rest
+                    if (FIB == MB_FIBERS_PYMUSCLE) cpf[i] = fatigue_update<true>(cpf[i], 0.0, fatdt[i], rdidt[i], ptf[i]);   // recovery, pmf:121-141
+                    emit(i, 0.0, false);
+                }
+                ftw[s * kW64Pitch + lane] = fsum;
+            };
+            switch (kon) {
+                case 0: body(std::integral_constant<int, 0>{}); break;
+                case 1: body(std::integral_constant<int, 1>{}); break;
+                case 2: if constexpr (UPL >= 2) body(std::integral_constant<int, 2>{}); break;
+                case 3: if constexpr (UPL >= 3) body(std::integral_constant<int, 3>{}); break;
+                default: if constexpr (UPL >= 4) body(std::integral_constant<int, 4>{}); break;
             }
-            ftw[s * kW64Pitch + lane] = fsum;
         };
         const bool has_last = a.forces_last != nullptr && tile == ntiles - 1;
         const int fast_steps = has_last ? steps - 1 : steps;
+#pragma unroll (kW64Unroll)
         for (int s = 0; s < fast_steps; ++s) do_step(s, std::false_type{});
         if (has_last) do_step(steps - 1, std::true_type{});
         __syncwarp();

@@ -109,9 +109,15 @@ struct K1sArgs {
 };
 
 // one unit, one step; state in, state out (no memory access)
+// FP32 mode: the capacity CHANGE of the step -- decay -fat*nf*dt (fibers:110-111) or, for a unit at rest, recovery
+// rec*((peak - c)/peak)*dt (pmf:121-141) -- is computed in float and added to the float64 state, which is what
+// "float per-step arithmetic, float64 state" means (the fused kernels do the same on their compensated pairs).  The
+// float64 form cost five FP64 instructions (two issue cycles each on B200) and two conversions per unit-step in a
+// kernel that ncu shows short of issue slots, not of HBM bandwidth.  fatdt / rdidt here are the float products
+// fat*dt and (rec/peak)*dt; a rested unit (c == peak) still gets exactly 0: (float)c == (float)peak.
 template <bool CENTRAL, bool RECOVERY>
 __device__ __forceinline__ float k1s_unit(const K1sArgs<float>& a, const UnitF& p, float x, double c, double d,
-                                          double fatdt, double rdidt, double ptf, double& cn, double& dn, const double*) {
+                                          float fatdt, float rdidt, double ptf, double& cn, double& dn, const double*) {
     bool on;
     float r = pool_rate_raw(p, a.sc, x, on);
     r = on ? r : 0.0f;                                                  // pool:171-172
@@ -121,8 +127,13 @@ __device__ __forceinline__ float k1s_unit(const K1sArgs<float>& a, const UnitF& 
         dn = duration_update(d, r > 0.0f, a.dt, a.max_dur);
     }
     float nf;
-    const float F = fibers_force(p, a.sc, fr, (float)c, nf);
-    cn = fatigue_update<RECOVERY>(c, (double)nf, fatdt, rdidt, ptf);
+    const float cf = (float)c;
+    const float F = fibers_force(p, a.sc, fr, cf, nf);
+    float delta = -nf * fatdt;                                          // fibers:110-111
+    if (RECOVERY) delta = (nf <= 0.0f) ? (p.ptf - cf) * rdidt : delta;  // pmf:121-141 (nf <= 0: the decay term is 0)
+    double cnew = zero_if_negative(c + (double)delta);                  // fibers:114
+    if (RECOVERY) cnew = (cnew > ptf) ? ptf : cnew;                     // pmf:104-105
+    cn = cnew;
     return F;
 }
 template <bool CENTRAL, bool RECOVERY>
@@ -146,6 +157,10 @@ __device__ __forceinline__ double k1s_unit(const K1sArgs<double>& a, const UnitD
     cn = fatigue_update<RECOVERY>(c, nf, fatdt, rdidt, ptf);
     return F;
 }
+
+// per-step rate constant x step size in the mode's arithmetic
+__device__ __forceinline__ float rate_dt(float rate, double dt) { return rate * (float)dt; }
+__device__ __forceinline__ double rate_dt(double rate, double dt) { return rate * dt; }
 
 // FP64 mode, first half of a unit-step: the adapted firing rate (and the new on-duration)
 template <bool CENTRAL>
@@ -181,8 +196,8 @@ k1_stream(const K1sArgs<T> a) {
     const int rowpi = W + 2 * kInAlign;                   // input row pitch (shift + round-up slack), a multiple of kInAlign
     constexpr int PR = PERROW ? R : 1;                    // parameter tiles per stage: one, or one per row (per-instance tables)
     T* in_s = (T*)(par_s + (size_t)NS * PR * G * W);      // [NS][R][rowpi] staged per-unit inputs (in_per_unit only)
-    double* redc0 = (double*)(in_s + (a.in_per_unit ? (size_t)NS * R * rowpi : 0));   // [2 item parities][R][8] capacity sums (float64)
-    T* red0 = (T*)(redc0 + 2 * R * 8);                                    // [2 item parities][R][8] force sums
+    T* redc0 = in_s + (a.in_per_unit ? (size_t)NS * R * rowpi : 0);       // [2 item parities][R][8] capacity deficits
+    T* red0 = redc0 + 2 * R * 8;                                          // [2 item parities][R][8] force sums
     // ragged rows: segment offsets and divisors are read once per work item by every thread ->
     // keep them in shared memory instead of paying a dependent global load per item
     double* segdiv_s = (double*)(red0 + 2 * R * 8);       // [S]
@@ -303,7 +318,7 @@ k1_stream(const K1sArgs<T> a) {
         const int n = seg_off ? seg_off[seg + 1] - off0 : (int)a.L;
         const int nrows = (int)min((int64_t)R, a.rows - r0);
         T xm[R], partial[R];
-        double csum[R];                                       // new capacities, float64 in both modes (muscle.py:248-256 sums float64)
+        T csum[R];                                            // lost capacity sum(peak - new capacity): 0 exactly for a rested muscle
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             partial[r] = 0;
@@ -323,7 +338,7 @@ k1_stream(const K1sArgs<T> a) {
             if (active) {
                 const P* pst = par_s + (size_t)(s * PR * G) * W;
                 auto p = load_unit_staged(pst, W, tid);
-                double fatdt = (double)p.fat * a.dt, rdidt = (double)p.rdi * a.dt;
+                auto fatdt = rate_dt(p.fat, a.dt), rdidt = rate_dt(p.rdi, a.dt);   // float in FP32 mode, double in FP64 mode
                 double ptf = unit_peak(p);
                 const double* cs = cpf_s + (s * R) * rowp + tid;
                 const double* ds = dur_s + (s * R) * rowp + tid;
@@ -345,8 +360,8 @@ k1_stream(const K1sArgs<T> a) {
                 auto row = [&](int r) {
                     if (PERROW && r > 0) {                           // per-instance tables: this row's own parameters
                         p = load_unit_staged(pst + (size_t)(r * G) * W, W, tid);
-                        fatdt = (double)p.fat * a.dt;
-                        rdidt = (double)p.rdi * a.dt;
+                        fatdt = rate_dt(p.fat, a.dt);
+                        rdidt = rate_dt(p.rdi, a.dt);
                         ptf = unit_peak(p);
                     }
                     const double c = ldc(r), d = ldd(r);
@@ -356,7 +371,7 @@ k1_stream(const K1sArgs<T> a) {
                     *cp = cn;
                     if (CENTRAL) *dp = dn;
                     partial[r] += F;
-                    if (want_fatigue) csum[r] += cn;
+                    if (want_fatigue) csum[r] += (T)(ptf - cn);
                     if (FORCES) fp += a.L;
                     cp += a.L;
                     if (CENTRAL) dp += a.L;
@@ -401,7 +416,7 @@ k1_stream(const K1sArgs<T> a) {
                                 *cp = cn;
                                 if (CENTRAL) *dp = dn[i];
                                 partial[r] += F;
-                                if (want_fatigue) csum[r] += cn;
+                                if (want_fatigue) csum[r] += (T)(ptf - cn);
                             }
                             if (FORCES) fp += a.L;
                             cp += a.L;
@@ -424,14 +439,14 @@ k1_stream(const K1sArgs<T> a) {
             // scratch alternates between consecutive items, so ONE barrier per item is enough: a warp
             // reaches the next write of the same half only after the barrier of the item in between
             T* red = red0 + (item_no & 1) * (R * 8);
-            double* redc = redc0 + (item_no & 1) * (R * 8);
+            T* redc = redc0 + (item_no & 1) * (R * 8);
             ++item_no;
             static_assert(R == 8, "warp_sum_rows8 reduces exactly eight rows");
             const int rr = (lane >> 2) & 7;                       // the row whose warp total this lane ends up with
             const T wf = warp_sum_rows8(partial, lane);
             if ((lane & 3) == 0) red[rr * 8 + warp] = wf;
             if (want_fatigue) {
-                const double wc = warp_sum_rows8(csum, lane);
+                const T wc = warp_sum_rows8(csum, lane);
                 if ((lane & 3) == 0) redc[rr * 8 + warp] = wc;
             }
             asm volatile("bar.sync 1, %0;" ::"r"(ncons) : "memory");
@@ -448,9 +463,12 @@ k1_stream(const K1sArgs<T> a) {
                     a.totals[mu] = sum;
                 }
                 if (want_fatigue) {
-                    double cs = redc[tid * 8];
+                    // 1 - sum(capacity)/max_arb_output (muscle.py:248-256) as sum(peak - capacity)/max_arb_output: the same
+                    // number for a StandardMuscle (max_arb_output = sum(peak), muscle.py:187) up to rounding, but exactly 0
+                    // for a rested muscle whatever the order of the parallel sum, and never negative
+                    T cs = redc[tid * 8];
                     for (int w = 1; w < ncw; ++w) cs += redc[tid * 8 + w];
-                    a.fatigue[mu] = 1.0 - cs / (seg_div ? seg_div[seg] : a.fat_div);
+                    a.fatigue[mu] = (double)cs / (seg_div ? seg_div[seg] : a.fat_div);
                 }
             }
         }

@@ -359,8 +359,23 @@ __global__ void __launch_bounds__(256, MINB) k1_step(const K1Args<T> a) {
 // =====================================================================================
 // K3: per-muscle capacity sums (StandardMuscle.get_peripheral_fatigue, muscle.py:248-256)
 // =====================================================================================
-__global__ void __launch_bounds__(256) k3_fatigue(int64_t rows, int64_t L, int32_t S, const int32_t* seg_off,
-                                                  const double* seg_div, const double* cpf, double* out,
+// fatigue = sum(peak - capacity) / max_arb_output: algebraically 1 - sum(capacity)/max_arb_output for a StandardMuscle
+// (max_arb_output = sum(peak), muscle.py:187), exactly 0 at rest whatever the summation order, never negative.
+template <typename PT>
+__device__ __forceinline__ double table_peak(const PT* params, int64_t L, int64_t i);
+template <>
+__device__ __forceinline__ double table_peak<float4>(const float4* P, int64_t L, int64_t i) {
+    const float4 c = __ldg(P + 2 * L + i);                // (ptf, ptf_lo2, rdi, ptf_lo)
+    return ((double)c.x + (double)c.w) + (double)c.y;
+}
+template <>
+__device__ __forceinline__ double table_peak<double2>(const double2* P, int64_t L, int64_t i) {
+    return __ldg(P + 3 * L + i).y;                        // (fat, ptf)
+}
+
+template <typename PT>
+__global__ void __launch_bounds__(256) k3_fatigue(const PT* params, int64_t param_stride, int64_t rows, int64_t L, int32_t S,
+                                                  const int32_t* seg_off, const double* seg_div, const double* cpf, double* out,
                                                   double out_div) {
     __shared__ double red[8];
     const int64_t n_muscles = rows * S;
@@ -369,15 +384,16 @@ __global__ void __launch_bounds__(256) k3_fatigue(int64_t rows, int64_t L, int32
         const int seg = (int)(mu - row * S);
         const int off0 = seg_off ? seg_off[seg] : 0;
         const int n = seg_off ? seg_off[seg + 1] - off0 : (int)L;
+        const PT* table = params + row * param_stride;
         double part = 0.0;
-        for (int u = threadIdx.x; u < n; u += blockDim.x) part += cpf[row * L + off0 + u];
+        for (int u = threadIdx.x; u < n; u += blockDim.x) part += table_peak<PT>(table, L, off0 + u) - cpf[row * L + off0 + u];
         part = warp_sum(part);
         if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
         __syncthreads();
         if (threadIdx.x == 0) {
             double s = 0.0;
             for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
-            out[mu] = 1.0 - s / (seg_div ? seg_div[seg] : out_div);
+            out[mu] = s / (seg_div ? seg_div[seg] : out_div);
         }
         __syncthreads();
     }
@@ -612,8 +628,13 @@ static bool k1s_eligible(const MbConfig& c, int64_t L, int32_t stage, int32_t in
 }
 
 // Rows of several muscles with one input per muscle: the flat-tiled kernel (mb_flat.cuh)
-static bool use_flat(const MbConfig& c, int32_t S, int32_t in_per_unit) {
-    return S > 1 && S <= kFlatMaxS && !in_per_unit && c.param_rows <= 1 && knobs().k1_flat != 0;
+// Measured on B200 (scripts/r2_ragged.py): flat tiling wins where muscles are short against a tile (hopper legs: +38 % FP32,
+// +48 % FP64; 8 x 256 units: +4..10 % FP32) and loses a few per cent where every muscle fills several tiles anyway.
+static bool use_flat(const MbConfig& c, int64_t L, int32_t S, int32_t in_per_unit) {
+    if (!(S > 1 && S <= kFlatMaxS && !in_per_unit && c.param_rows <= 1) || knobs().k1_flat == 0) return false;
+    if (knobs().k1_flat > 0) return true;
+    const int64_t mean_n = L / S;
+    return mean_n <= (c.precision == MB_F32 ? 512 : 192);
 }
 
 extern "C" int mb_step(const MbConfig* cfg, const void* params_dev, int64_t rows, int64_t L, int32_t S,
@@ -634,13 +655,13 @@ extern "C" int mb_step(const MbConfig* cfg, const void* params_dev, int64_t rows
     const K1sEpilogue no_epilogue;
     if (cfg->precision == MB_F32) {
         if (k1s_eligible<float>(*cfg, L, stage, in_per_unit, in_dev, cpf_dev, dur_dev, mask_dev, rates_dev, forces_dev))
-            return (use_flat(*cfg, S, in_per_unit) ? launch_k1f_f32 : launch_k1s_f32)(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, in_dev, in_per_unit, cpf_dev,
+            return (use_flat(*cfg, L, S, in_per_unit) ? launch_k1f_f32 : launch_k1s_f32)(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, in_dev, in_per_unit, cpf_dev,
                                   dur_dev, forces_dev, totals_dev, no_epilogue, step_size, st);
         return launch_k1<float>(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, stage, in_dev, in_per_unit, cpf_dev,
                                 dur_dev, forces_dev, totals_dev, mask_dev, rates_dev, step_size, st, scal_f(*cfg));
     }
     if (k1s_eligible<double>(*cfg, L, stage, in_per_unit, in_dev, cpf_dev, dur_dev, mask_dev, rates_dev, forces_dev))
-        return (use_flat(*cfg, S, in_per_unit) ? launch_k1f_f64 : launch_k1s_f64)(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, in_dev, in_per_unit, cpf_dev,
+        return (use_flat(*cfg, L, S, in_per_unit) ? launch_k1f_f64 : launch_k1s_f64)(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, in_dev, in_per_unit, cpf_dev,
                               dur_dev, forces_dev, totals_dev, no_epilogue, step_size, st);
     return launch_k1<double>(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, stage, in_dev, in_per_unit, cpf_dev, dur_dev,
                              forces_dev, totals_dev, mask_dev, rates_dev, step_size, st, scal_d(*cfg));
@@ -663,13 +684,13 @@ static int step_env_impl(const MbConfig* cfg, const void* params_dev, int64_t ro
     if (cfg->precision == MB_F32) {
         if (!k1s_eligible<float>(*cfg, L, MB_STAGE_MUSCLE, 0, in_dev, cpf_dev, dur_dev, nullptr, nullptr, forces_dev, ep.fatigue))
             return fail(MB_EUNSUPPORTED, "mb_step_env needs 16-byte aligned state arrays and peripheral fatigue on");
-        return (use_flat(*cfg, S, 0) ? launch_k1f_f32 : launch_k1s_f32)(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev,
+        return (use_flat(*cfg, L, S, 0) ? launch_k1f_f32 : launch_k1s_f32)(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev,
                                                                         in_dev, 0, cpf_dev, dur_dev, forces_dev, totals_dev,
                                                                         ep, step_size, st);
     }
     if (!k1s_eligible<double>(*cfg, L, MB_STAGE_MUSCLE, 0, in_dev, cpf_dev, dur_dev, nullptr, nullptr, forces_dev, ep.fatigue))
         return fail(MB_EUNSUPPORTED, "mb_step_env needs 16-byte aligned state arrays and peripheral fatigue on");
-    return (use_flat(*cfg, S, 0) ? launch_k1f_f64 : launch_k1s_f64)(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, in_dev,
+    return (use_flat(*cfg, L, S, 0) ? launch_k1f_f64 : launch_k1s_f64)(*cfg, params_dev, rows, L, S, seg_off_dev, seg_div_dev, in_dev,
                                                                     0, cpf_dev, dur_dev, forces_dev, totals_dev, ep, step_size, st);
 }
 
@@ -702,17 +723,23 @@ extern "C" int mb_step_env_hill(const MbConfig* cfg, const void* params_dev, int
                          totals_dev, ep, step_size, stream);
 }
 
-extern "C" int mb_peripheral_fatigue(const MbConfig* cfg, int64_t rows, int64_t L, int32_t S,
+extern "C" int mb_peripheral_fatigue(const MbConfig* cfg, const void* params_dev, int64_t rows, int64_t L, int32_t S,
                                      const int32_t* seg_off_dev, const double* seg_div_dev, const double* cpf_dev, double* fatigue_dev,
                                      void* stream) {
     if (int rc = check_cfg(cfg)) return rc;
-    if (rows <= 0 || L <= 0 || S <= 0 || !cpf_dev || !fatigue_dev) return fail(MB_EINVAL, "mb_peripheral_fatigue: bad argument");
+    if (rows <= 0 || L <= 0 || S <= 0 || !params_dev || !cpf_dev || !fatigue_dev) return fail(MB_EINVAL, "mb_peripheral_fatigue: bad argument");
     if (S > 1 && !seg_off_dev) return fail(MB_EINVAL, "mb_peripheral_fatigue: seg_off required when S > 1");
     int64_t blocks = rows * S;
     const int64_t cap = (int64_t)sm_count() * 16;
     if (blocks > cap) blocks = cap;
-    k3_fatigue<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(rows, L, S, seg_off_dev, seg_div_dev, cpf_dev,
-                                                                   fatigue_dev, cfg->output_divisor);
+    if (cfg->precision == MB_F32)
+        k3_fatigue<float4><<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(
+            (const float4*)params_dev, cfg->param_rows > 1 ? (int64_t)kGroupsF32 * L : 0, rows, L, S, seg_off_dev, seg_div_dev,
+            cpf_dev, fatigue_dev, cfg->output_divisor);
+    else
+        k3_fatigue<double2><<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(
+            (const double2*)params_dev, cfg->param_rows > 1 ? (int64_t)kGroupsF64 * L : 0, rows, L, S, seg_off_dev, seg_div_dev,
+            cpf_dev, fatigue_dev, cfg->output_divisor);
     MB_CUDA_OK(cudaGetLastError());
     return MB_OK;
 }
@@ -887,6 +914,7 @@ extern "C" int mb_step_fused_ex(const MbConfig* cfg, const void* params_dev, con
     a.dm1 = a.decay - 1.0f;                                  // exact in float (Sterbenz)
     a.sf = scal_f(*cfg);
     a.sd = scal_d(*cfg);
+    a.ec = exp_consts();
 
     // central-fatigue variant (see k2_fused_f32): the fast path needs the packed table's
     // MB_PROP_ADAPT_NONNEG guarantee and a duration clamp that exp(-dur/tau) cannot see

@@ -556,7 +556,7 @@ class MuscleBatch:
         out = torch.empty(self.rows, self.S, dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):
             nat.check(nat.lib().mb_peripheral_fatigue(
-                C.byref(self.cfg), self.rows, self.L, self.S, _ptr(self._seg_off), _ptr(self._seg_div),
+                C.byref(self.cfg), _ptr(self._params), self.rows, self.L, self.S, _ptr(self._seg_off), _ptr(self._seg_div),
                 _ptr(self.cpf), _ptr(out), self._stream()))
         self.launches += 1
         return self._shape_out(out)

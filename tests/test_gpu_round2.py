@@ -272,7 +272,14 @@ def test_fused_fatigue_is_exactly_zero_at_rest_and_equals_the_standalone_kernel(
     for _ in range(30):
         _, fat = b.step_env(torch.rand(rows, 3, device=cuda_device, generator=g, dtype=b.dtype), dt)
     alone = b.get_peripheral_fatigue()
-    torch.testing.assert_close(fat, alone, rtol=1e-12, atol=1e-15)     # both sum float64 capacities; order may differ
+    # (the fused readout sums the lost capacity in the mode's arithmetic, the stand-alone kernel in float64)
+    tol = dict(rtol=1e-12, atol=1e-15) if precision == "f64" else dict(rtol=2e-6, atol=1e-9)
+    torch.testing.assert_close(fat, alone, **tol)
+    off = np.concatenate([[0], np.cumsum([sp.n for sp in specs])])
+    cpf = b.cpf.cpu().numpy()
+    ref = np.stack([1.0 - np.array([sum(cpf[r, off[i]:off[i + 1]]) for r in range(rows)]) / specs[i].output_divisor
+                    for i in range(3)], axis=1)                       # muscle.py:248-256, built-in sequential sum
+    np.testing.assert_allclose(alone.cpu().numpy(), ref, rtol=1e-9, atol=1e-14)
     assert (fat > 0).all()
 
 
