@@ -273,6 +273,34 @@ __device__ __forceinline__ void pair_store(PairState& st, int k, const K2Args& a
     }
 }
 
+// write element k of a pair back WITHOUT reading the old state (persistent short-window kernel): the capacity is the
+// exact sum of the float pair (48 bits), except that a unit sitting at its peak -- rested, or recovered up to the clamp
+// pmf:104-105 -- gets the exact float64 peak; the on-duration is advanced by a fire-and-forget atomic add of count * dt
+// (no clamp can trigger far below max_duration; near it, the slow read-modify-write path runs).
+template <bool CENTRAL, typename PT>
+__device__ __forceinline__ void pair_store_direct(PairState& st, const PairParams<PT>& p, int k, const K2Args& a, int64_t idx,
+                                                  float ptf_lo2) {
+    if (a.peripheral) {
+        const float hi = el(st.hi, k), lo = el(st.lo, k);
+        const float ptf = k ? LY(p.ptf) : LX(p.ptf), ptf_lo = k ? LY(p.ptf_lo) : LX(p.ptf_lo);
+        const double exact_peak = ((double)ptf + (double)ptf_lo) + (double)ptf_lo2;
+        a.cpf[idx] = (hi == ptf && lo == ptf_lo) ? exact_peak : (double)hi + (double)lo;
+    }
+    if (CENTRAL) {
+        const float cnt = el(st.cnt, k);
+        if (cnt > 0.0f) {
+            const double add = (double)cnt * a.dt;
+            const double d0_est = (double)el(st.arg0, k) / a.adk_d;            // start value to float accuracy
+            if (d0_est + add < 0.99 * a.max_dur) {
+                atomicAdd(&a.dur[idx], add);                                   // (result unused: RED.ADD.F64)
+            } else {
+                double d = fma((double)cnt, a.dt, a.dur[idx]);
+                a.dur[idx] = (d > a.max_dur) ? a.max_dur : d;                  // pool:202-203
+            }
+        }
+    }
+}
+
 __device__ __forceinline__ PairScal pair_scal(const K2Args& a) {
     PairScal s;
     s.gain_e = a.sf.gain_e; s.c25k = a.sf.c25k; s.ythr = a.sf.ythr; s.argmin = a.sf.argmin;
@@ -342,6 +370,9 @@ struct CoreF32 {
     }
     __device__ __forceinline__ void store(int j, const K2Args& a, int64_t idx) {
         pair_store<CENTRAL != 0>(st[j >> 1], j & 1, a, idx);
+    }
+    __device__ __forceinline__ void store_direct(int j, const K2Args& a, int64_t idx, float ptf_lo2) {
+        pair_store_direct<CENTRAL != 0>(st[j >> 1], p, j & 1, a, idx, ptf_lo2);
     }
     __device__ __forceinline__ float out_scale(float v) const { return v * inv_out; }
 };

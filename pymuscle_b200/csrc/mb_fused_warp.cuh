@@ -30,22 +30,67 @@ constexpr int kWarpsPerBlock = 8;
 #ifndef MB_W_MINB
 #define MB_W_MINB 2
 #endif
-template <int FIB, int CENTRAL, int UPL, bool FORCES>
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+
+// PERSIST (short windows): with K = 8..128 steps per launch a muscle pair is a few microseconds of arithmetic between
+// two round trips to HBM -- state in, state out -- and ncu shows a third of the warp samples waiting on exactly those
+// loads (K = 32: 258 us against 182 us of arithmetic).  The persistent variant launches only the resident warps; each
+// walks a strided list of muscle pairs and, while it advances pair j, has the state of pair j+1 copied into its own
+// shared-memory stage by cp.async (the stage is free as soon as pair j's state is in registers).  At the end of a pair
+// nothing is read back: capacities are stored from the compensated float pair (a unit that sits at its peak gets the
+// exact float64 peak, so rested units keep their bits) and on-durations are advanced by a fire-and-forget
+// red.add.f64 of count * dt.
+template <int FIB, int CENTRAL, int UPL, bool FORCES, bool PERSIST = false>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, MB_W_MINB) k2w_f32(const K2Args a) {
     using Core = CoreF32<FIB, CENTRAL, 2>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float2* ftw = (float2*)smem_raw + warp * (kWTile * kWPitch + 2 * kWTile);   // [32][33]
+    constexpr int kPerWarp = kWTile * kWPitch + 2 * kWTile;                      // float2 elements: force tile + excitations
+    float2* ftw = (float2*)smem_raw + warp * kPerWarp;                           // [32][33]
     float2* excw = ftw + kWTile * kWPitch;                                       // [2][32]
-
     const int n = a.n;
-    const int64_t m0 = ((int64_t)blockIdx.x * kWarpsPerBlock + warp) * 2;
-    if (m0 >= a.M) return;                                // warps are independent: no barrier below
-    const bool two = m0 + 1 < a.M;
+    // PERSIST: per-warp stage [2][2n] doubles (capacities | durations of the NEXT pair), behind all warps' tiles
+    double* stage = (double*)((float2*)smem_raw + kWarpsPerBlock * kPerWarp) + (size_t)warp * 4 * ((n + 1) & ~1);
+    const int stage_n = 2 * ((n + 1) & ~1);                                      // doubles per array in the stage
+
+    const int64_t npairs = (a.M + 1) >> 1;
+    const int64_t first = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
+    const int64_t stride = PERSIST ? (int64_t)gridDim.x * kWarpsPerBlock : npairs;   // (not PERSIST: exactly one pair per warp)
+    if (first >= npairs) return;                          // warps are independent: no block barrier below
     const int ntiles = (a.K + kWTile - 1) / kWTile;
     const float* exc = (const float*)a.exc;
 
+    auto prefetch = [&](int64_t pair) {                   // state of `pair` -> this warp's stage (cp.async, one group)
+        const int64_t m0 = pair * 2;
+        const int cnt = (m0 + 1 < a.M) ? 2 * n : n;       // units to fetch; m0 even => the source is 16-byte aligned
+        const uint32_t sc = smem_u32(stage), sd = smem_u32(stage + stage_n);
+        for (int i = lane; i < (cnt >> 1); i += 32) {
+            cp_async16(sc + 16u * i, a.cpf + m0 * n + 2 * i);
+            if (CENTRAL) cp_async16(sd + 16u * i, a.dur + m0 * n + 2 * i);
+        }
+        if ((cnt & 1) && lane == 0) {
+            cp_async8(sc + 8u * (cnt - 1), a.cpf + m0 * n + cnt - 1);
+            if (CENTRAL) cp_async8(sd + 8u * (cnt - 1), a.dur + m0 * n + cnt - 1);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (PERSIST) prefetch(first);
+
+    for (int64_t pair = first; pair < npairs; pair += stride) {
+    const int64_t m0 = pair * 2;
+    const bool two = m0 + 1 < a.M;
+
     Core core[UPL];
+    if (PERSIST) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+    }
 #pragma unroll
     for (int i = 0; i < UPL; ++i) {
         const int u = lane + 32 * i;
@@ -53,9 +98,18 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MB_W_MINB) k2w_f32(const 
         core[i].load(a, valid ? u : 0, 0);
         if (!valid) core[i].disable();                                  // idle slot: never recruited, force 0
         if (valid) {
-            core[i].init(0, a, a.cpf[m0 * n + u], CENTRAL ? a.dur[m0 * n + u] : 0.0);
-            if (two) core[i].init(1, a, a.cpf[(m0 + 1) * n + u], CENTRAL ? a.dur[(m0 + 1) * n + u] : 0.0);
+            if (PERSIST) {
+                core[i].init(0, a, stage[u], CENTRAL ? stage[stage_n + u] : 0.0);
+                if (two) core[i].init(1, a, stage[n + u], CENTRAL ? stage[stage_n + n + u] : 0.0);
+            } else {
+                core[i].init(0, a, a.cpf[m0 * n + u], CENTRAL ? a.dur[m0 * n + u] : 0.0);
+                if (two) core[i].init(1, a, a.cpf[(m0 + 1) * n + u], CENTRAL ? a.dur[(m0 + 1) * n + u] : 0.0);
+            }
         }
+    }
+    if (PERSIST) {
+        __syncwarp();                                     // every lane has its state in registers: the stage is free
+        if (pair + stride < npairs) prefetch(pair + stride);
     }
 
     // excitations of (tile, step = lane) for the two muscles; 0 beyond the window / batch
@@ -165,10 +219,17 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MB_W_MINB) k2w_f32(const 
     for (int i = 0; i < UPL; ++i) {
         const int u = lane + 32 * i;
         if (u < n) {
-            core[i].store(0, a, m0 * n + u);
-            if (two) core[i].store(1, a, (m0 + 1) * n + u);
+            if (PERSIST) {
+                const float lo2 = __ldg((const float4*)a.params + 2 * (int64_t)n + u).y;   // third float of the peak (L2)
+                core[i].store_direct(0, a, m0 * n + u, lo2);
+                if (two) core[i].store_direct(1, a, (m0 + 1) * n + u, lo2);
+            } else {
+                core[i].store(0, a, m0 * n + u);
+                if (two) core[i].store(1, a, (m0 + 1) * n + u);
+            }
         }
     }
+    }   // pair loop
 }
 
 // ======================================================================================

@@ -33,6 +33,7 @@ struct Knobs {
     int fused_no_bulk;   // MB_FUSED_NO_BULK=1  block kernel stages excitations with plain loads
     int fused_general;   // MB_FUSED_GENERAL=1  fused kernels keep every clamp of the reference
     int f64_block;       // MB_F64_BLOCK=1      FP64 mode: block kernel where it would pick the warp kernel
+    int fused_persist;   // MB_FUSED_PERSIST    -1 auto (windows of <= 256 steps), 0 never, 1 always: persistent short-window warp kernel
     int fused_wide;      // MB_FUSED_WIDE=1     FP32 mode, n > 128: block-per-muscle kernel where it would pick the block kernel
 };
 const Knobs& knobs();
@@ -76,7 +77,8 @@ enum FusedKernel {
     FK_WARP_PAIR = 1,    // k2w_f32: one warp per muscle pair (12..128 units)
     FK_WARP_UNITS = 2,   // k2u_f32: one warp per muscle, pairs of units (per-instance tables)
     FK_WARP_F64 = 3,     // k2w_f64: one warp per muscle, FP64 mode (n <= 128)
-    FK_WIDE = 4          // k2x_f32: one block per muscle, any n (wide muscles, ragged rows)
+    FK_WIDE = 4,         // k2x_f32: one block per muscle, any n (wide muscles, ragged rows)
+    FK_WARP_PAIR_PERSIST = 5   // k2w_f32<PERSIST>: short windows -- resident warps walk the pairs, state prefetched by cp.async
 };
 
 }  // namespace mb

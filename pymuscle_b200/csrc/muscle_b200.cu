@@ -54,6 +54,7 @@ const Knobs& mb::knobs() {
         q.fused_general = env_int("MB_FUSED_GENERAL", 0);
         q.f64_block = env_int("MB_F64_BLOCK", 0);
         q.fused_wide = env_int("MB_FUSED_WIDE", 0);
+        q.fused_persist = env_int("MB_FUSED_PERSIST", -1);
         return q;
     }();
     return k;
@@ -749,7 +750,7 @@ static const int kFusedMaxUnits = 480;     // threads per block <= 480 (15 warps
 static const int kWideMaxUnits = 4096;     // block-per-muscle kernel: 512 threads x 4 pairs of units
 
 static int fused_geometry(const MbConfig& c, int64_t M, int32_t n, int32_t K, int32_t upt, FusedGeom* g,
-                          bool forces = false) {
+                          bool forces = false, bool state_aligned16 = true) {
     if (n < 2 || n > kFusedMaxUnits)
         return fail(MB_EUNSUPPORTED, "fused kernel supports 2 <= n <= %d units per muscle (got %d)", kFusedMaxUnits, n);
     if (M <= 0 || K <= 0) return fail(MB_EINVAL, "M and K must be positive");
@@ -788,6 +789,15 @@ static int fused_geometry(const MbConfig& c, int64_t M, int32_t n, int32_t K, in
         g->threads = kWarpsPerBlock * 32;
         g->smem = kWarpsPerBlock * (kWTile * kWPitch + 2 * kWTile) * (int)sizeof(float2);
         g->blocks = (M + g->G - 1) / g->G;
+        // short windows without force capture: resident warps walk the pairs and prefetch the next pair's state
+        const int persist = knobs().fused_persist;
+        const int64_t resident = 2LL * sm_count();
+        if (!forces && state_aligned16 && c.param_rows <= 1 && g->blocks > resident &&
+            (persist > 0 || (persist < 0 && K <= 256))) {
+            g->kernel = FK_WARP_PAIR_PERSIST;
+            g->smem += kWarpsPerBlock * 4 * ((n + 1) & ~1) * (int)sizeof(double);
+            g->blocks = resident;
+        }
         return MB_OK;
     }
     const int ns = (n + 7) / 8 * 8;                          // threads per muscle group (stage-1 parts are 8 wide)
@@ -869,7 +879,8 @@ extern "C" int mb_step_fused_ex(const MbConfig* cfg, const void* params_dev, con
         g.q = 1; g.G = 1; g.Gp = 1; g.T = kXTile; g.ns = maxn; g.npg = 0; g.ptp = 0;
         g.smem = (nw * (kXTile * kXPitch + 2 * kXTile) + 2 * kXTile * (nw + 1)) * (int)sizeof(float);
         g.blocks = M;
-    } else if (int rc = fused_geometry(*cfg, M, n, K, w->units_per_thread, &g, w->forces_every > 0)) {
+    } else if (int rc = fused_geometry(*cfg, M, n, K, w->units_per_thread, &g, w->forces_every > 0,
+                                       ((uintptr_t)w->cpf_dev % 16 == 0) && ((uintptr_t)w->dur_dev % 16 == 0))) {
         return rc;
     }
     const bool f32 = cfg->precision == MB_F32;
@@ -936,7 +947,7 @@ extern "C" int mb_step_fused_ex(const MbConfig* cfg, const void* params_dev, con
         return launch_k2x_f32(xa, g, fib, cen, forces, st);
     }
     if (g.kernel == FK_WARP_UNITS) return launch_k2u_f32(a, g, fib, cen, forces, st);
-    if (g.kernel == FK_WARP_PAIR) return launch_k2w_f32(a, g, fib, cen, forces, st);
+    if (g.kernel == FK_WARP_PAIR || g.kernel == FK_WARP_PAIR_PERSIST) return launch_k2w_f32(a, g, fib, cen, forces, st);
     if (f32) return launch_k2_block_f32(a, g, fib, cen, forces, st);
     // FP64: the fast path additionally needs the sigmoid's exponent bounded (no clamp in exp_neg_fast);
     // without central fatigue the clamp is kept (CENTRAL == 0 instantiates it)
