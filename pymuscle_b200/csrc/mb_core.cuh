@@ -7,6 +7,16 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// MB_BOUNDS build (make bounds -> libmuscle_b200_bounds.so): device-side asserts on the index of every state / output
+// access and on the shared-memory slots that depend on the batch layout.  compute-sanitizer is not available on the
+// GPU pool, so one pytest target (tests/test_gpu_bounds.py) runs the odd-sized and ragged shapes through this build.
+#ifdef MB_BOUNDS
+#include <cassert>
+#define MB_ASSERT(cond) assert(cond)
+#else
+#define MB_ASSERT(cond) ((void)0)
+#endif
+
 namespace mb {
 
 // ----------------------------------------------------------------------------------

@@ -191,6 +191,7 @@ k1_flat(const K1fArgs<T> fa) {
 #pragma unroll
             for (int r = 0; r < R; ++r) t[r] = mine ? partial[r] : T(0);
             const T wf = warp_sum_rows8(t, lane);
+            MB_ASSERT(sl >= 0 && sl < NSG);
             if ((lane & 3) == 0) af[sl * R + rr] += wf;
             if (FATIGUE) {
                 T tc[R];
@@ -227,6 +228,8 @@ k1_flat(const K1fArgs<T> fa) {
                 const double* ds = dur_s + (s * R) * rowp + tid;
                 const T* xs = xin_s + (size_t)s * R * NSG + (seg - sg0);
                 const int64_t i0 = r0 * a.L + c;
+                MB_ASSERT(c < a.L && seg >= sg0 && seg - sg0 < nsg && nsg <= NSG && tid < W &&
+                          i0 + (int64_t)(nrows - 1) * a.L < a.rows * a.L);
                 T* fp = FORCES ? a.forces + i0 : nullptr;
                 double* cp = a.cpf + i0;
                 double* dp = CENTRAL ? a.dur + i0 : nullptr;
@@ -264,6 +267,7 @@ k1_flat(const K1fArgs<T> fa) {
             const int r = q / nsg, sl = q - r * nsg;
             const int sg = sg0 + sl;
             const int64_t mu = (r0 + r) * S + sg;
+            MB_ASSERT(sg < S && mu < a.rows * S && sl < NSG);
             const T* f0 = accf + (size_t)(buf * ncw) * NSG * R + sl * R + r;
             if (a.totals) {
                 T sum = f0[0];

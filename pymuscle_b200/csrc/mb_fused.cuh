@@ -602,6 +602,7 @@ __device__ __forceinline__ void k2_body(const K2Args& a) {
         const int g = tq * U + j;
         if (has_unit && g < gcount) {
             const int64_t idx = (m0 + g) * n + u;
+            MB_ASSERT(idx < a.M * (int64_t)n && u < n);
             core.init(j, a, a.cpf[idx], Core::kCentral ? a.dur[idx] : 0.0);
         }
     }

@@ -82,11 +82,19 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MB_W_MINB) k2w_f32(const 
     };
     if (PERSIST) prefetch(first);
 
+    // unit parameters: the same for every pair this warp advances -- loaded (L2) and converted once
+    Core core[UPL];
+#pragma unroll
+    for (int i = 0; i < UPL; ++i) {
+        const int u = lane + 32 * i;
+        core[i].load(a, u < n ? u : 0, 0);
+        if (u >= n) core[i].disable();                                  // idle slot: never recruited, force 0
+    }
+
     for (int64_t pair = first; pair < npairs; pair += stride) {
     const int64_t m0 = pair * 2;
     const bool two = m0 + 1 < a.M;
-
-    Core core[UPL];
+    MB_ASSERT(m0 < a.M && (int64_t)(m0 + (two ? 2 : 1)) * n <= a.M * (int64_t)n);
     if (PERSIST) {
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
@@ -94,13 +102,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MB_W_MINB) k2w_f32(const 
 #pragma unroll
     for (int i = 0; i < UPL; ++i) {
         const int u = lane + 32 * i;
-        const bool valid = u < n;
-        core[i].load(a, valid ? u : 0, 0);
-        if (!valid) core[i].disable();                                  // idle slot: never recruited, force 0
-        if (valid) {
+        if (u < n) {
             if (PERSIST) {
                 core[i].init(0, a, stage[u], CENTRAL ? stage[stage_n + u] : 0.0);
-                if (two) core[i].init(1, a, stage[n + u], CENTRAL ? stage[stage_n + n + u] : 0.0);
+                // (a batch with an odd muscle count: the idle second half mirrors the first, its outputs are never stored)
+                core[i].init(1, a, stage[two ? n + u : u], CENTRAL ? stage[stage_n + (two ? n + u : u)] : 0.0);
             } else {
                 core[i].init(0, a, a.cpf[m0 * n + u], CENTRAL ? a.dur[m0 * n + u] : 0.0);
                 if (two) core[i].init(1, a, a.cpf[(m0 + 1) * n + u], CENTRAL ? a.dur[(m0 + 1) * n + u] : 0.0);
@@ -191,6 +197,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MB_W_MINB) k2w_f32(const 
             const float2 acc = __fadd2_rn(acc0, acc1);
             if (a.totals) {
                 const int64_t o = krow * a.totals_stride_k + m0;
+                MB_ASSERT(krow < (a.K + a.totals_every - 1) / a.totals_every && m0 < a.M);
                 const float t0 = core[0].out_scale(acc.x), t1 = core[0].out_scale(acc.y);
                 float* t = (float*)a.totals + o;
                 t[0] = t0;
@@ -258,6 +265,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (FIB == MB_FIBERS_PYMUSCL
     const int n = a.n;
     const int64_t m = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
     if (m >= a.M) return;                                 // warps are independent: no barrier below
+    MB_ASSERT(n <= 64 * NPU);
     const int ntiles = (a.K + kWTile - 1) / kWTile;
     const float* exc = (const float*)a.exc;
     const PairScal sc = pair_scal(a);

@@ -52,6 +52,7 @@ k2w_f64(const K2Args a) {
     const int n = a.n;
     const int64_t m = (int64_t)blockIdx.x * kW64Warps + warp;
     if (m >= a.M) return;                                  // warps are independent: no barrier below
+    MB_ASSERT(n <= 32 * UPL);
     const int ntiles = (a.K + kW64Tile - 1) / kW64Tile;
     const double* exc = (const double*)a.exc;
     const double2* table = (const double2*)a.params + m * a.param_stride;        // (per-instance tables: this muscle's own)
@@ -238,6 +239,7 @@ k2w_f64(const K2Args a) {
             }
             const double v = ((acc0 + acc1) + (acc2 + acc3)) / sc.out_div;        // muscle.py:278
             const int64_t krow = kl / a.totals_every;
+            MB_ASSERT(krow < (a.K + a.totals_every - 1) / a.totals_every);
             ((double*)a.totals)[krow * a.totals_stride_k + m] = v;
             if (a.n_peers > 0) {                                                  // peer GPUs' gather buffers (NVLink stores)
                 const int64_t op = (m >> 1) * a.peer_stride_pair + krow * a.peer_stride_k + (m & 1);

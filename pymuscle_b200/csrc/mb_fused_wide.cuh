@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1) k2x_f32(const
     const float4* table = (const float4*)a.params + (a.param_stride ? m * a.param_stride : 0);
     const int64_t tabL = xa.L;                             // table row length ([group][L])
     const int npa = (n + 2 * THREADS - 1) / (2 * THREADS); // pairs per thread this muscle needs (block-uniform)
+    MB_ASSERT(npa <= NPU && m < a.M && seg < xa.S && base + n <= xa.total_units && off0 + n <= xa.L);
     const int ntiles = (a.K + kXTile - 1) / kXTile;
     const float* exc = (const float*)a.exc;
     const PairScal sc = pair_scal(a);

@@ -33,7 +33,7 @@ struct Knobs {
     int fused_no_bulk;   // MB_FUSED_NO_BULK=1  block kernel stages excitations with plain loads
     int fused_general;   // MB_FUSED_GENERAL=1  fused kernels keep every clamp of the reference
     int f64_block;       // MB_F64_BLOCK=1      FP64 mode: block kernel where it would pick the warp kernel
-    int fused_persist;   // MB_FUSED_PERSIST    -1 auto (windows of <= 256 steps), 0 never, 1 always: persistent short-window warp kernel
+    int fused_persist;   // MB_FUSED_PERSIST    -1 auto (windows of <= 24 steps), 0 never, 1 always: persistent short-window warp kernel
     int fused_wide;      // MB_FUSED_WIDE=1     FP32 mode, n > 128: block-per-muscle kernel where it would pick the block kernel
 };
 const Knobs& knobs();

@@ -354,6 +354,7 @@ k1_stream(const K1sArgs<T> a) {
                     for (int r = 0; r < R; ++r) xm[r] = xs[r * rowpi + ((r * lm + em) & (kInAlign - 1))];
                 }
                 const int64_t i0 = r0 * a.L + off0 + u;
+                MB_ASSERT(u < n && off0 + u < a.L && i0 + (int64_t)(nrows - 1) * a.L < a.rows * a.L && tid < W);
                 T* fp = FORCES ? a.forces + i0 : nullptr;
                 double* cp = a.cpf + i0;
                 double* dp = CENTRAL ? a.dur + i0 : nullptr;
@@ -452,6 +453,7 @@ k1_stream(const K1sArgs<T> a) {
             asm volatile("bar.sync 1, %0;" ::"r"(ncons) : "memory");
             if (tid < nrows) {
                 const int64_t mu = (r0 + tid) * a.S + seg;
+                MB_ASSERT(mu < a.rows * a.S && seg < a.S);
                 if (a.totals) {
                     T sum = red[tid * 8];
                     for (int w = 1; w < ncw; ++w) sum += red[tid * 8 + w];

@@ -310,6 +310,7 @@ __global__ void __launch_bounds__(256, MINB) k1_step(const K1Args<T> a) {
         for (int u = tx; u < n; u += TX) {
             auto p = load_unit(a.params + r0 * a.param_stride, a.L, off0 + u);
             const int64_t i0 = r0 * a.L + off0 + u;
+            MB_ASSERT(off0 + u < a.L && i0 + (int64_t)(nrows - 1) * a.L < a.rows * a.L);
             double c[R], d[R];
             T x[R];
 #pragma unroll
@@ -789,11 +790,14 @@ static int fused_geometry(const MbConfig& c, int64_t M, int32_t n, int32_t K, in
         g->threads = kWarpsPerBlock * 32;
         g->smem = kWarpsPerBlock * (kWTile * kWPitch + 2 * kWTile) * (int)sizeof(float2);
         g->blocks = (M + g->G - 1) / g->G;
-        // short windows without force capture: resident warps walk the pairs and prefetch the next pair's state
+        // very short windows without force capture: resident warps walk the pairs and prefetch the next pair's state.
+        // Measured (Potvin 120 x 65,536, us per window, one-pair-per-warp / persistent): K = 8: 162 / 128, K = 16: 199 / 173,
+        // K = 32: 264 / 266, K = 64: 418 / 464 -- the persistent loop is ~9 % slower per step, so it only pays while the
+        // window is dominated by the state round trip
         const int persist = knobs().fused_persist;
         const int64_t resident = 2LL * sm_count();
         if (!forces && state_aligned16 && c.param_rows <= 1 && g->blocks > resident &&
-            (persist > 0 || (persist < 0 && K <= 256))) {
+            (persist > 0 || (persist < 0 && K <= 24))) {
             g->kernel = FK_WARP_PAIR_PERSIST;
             g->smem += kWarpsPerBlock * 4 * ((n + 1) & ~1) * (int)sizeof(double);
             g->blocks = resident;
