@@ -255,6 +255,13 @@ typedef struct MbFusedArgs {
     int32_t n_peers;
     int32_t max_segment_units;   /* S > 1: the longest muscle of a row (the host knows seg_off; the library only has the device copy) */
     int64_t peer_stride_k, peer_stride_pair;
+    int64_t peer_stride_odd;     /* stride of the odd muscle of a pair in a peer buffer (0 = 1): element (k, m) lives at
+                                    (m >> 1) * peer_stride_pair + k * peer_stride_k + (m & 1) * peer_stride_odd, so that
+                                    (stride_k, stride_pair, stride_odd) = (1, 2 * K_max, K_max) is the muscle-major layout in which
+                                    the FP64 warp kernel (one warp per muscle) stores 256 contiguous bytes per 32 steps */
+    int32_t peer_multicast;      /* 1: peer_totals_dev[0] is an NVLink multicast address (n_peers == 1): every total leaves this
+                                    GPU once (multimem.st) and the NVSwitch replicates it into all GPUs' gather buffers */
+    int32_t reserved;
 } MbFusedArgs;
 int mb_step_fused_ex(const MbConfig* cfg, const void* params_dev, const MbFusedArgs* args,
                      double step_size, void* stream);

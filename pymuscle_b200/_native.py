@@ -87,6 +87,8 @@ class MbFusedArgs(C.Structure):
         ("n_peers", C.c_int32),
         ("max_segment_units", C.c_int32),
         ("peer_stride_k", C.c_int64), ("peer_stride_pair", C.c_int64),
+        ("peer_stride_odd", C.c_int64),
+        ("peer_multicast", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

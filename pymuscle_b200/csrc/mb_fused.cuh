@@ -61,7 +61,8 @@ struct K2Args {
     int64_t totals_stride_k;
     void* totals_peer[kMaxPeers];  // further copies of the totals (same stride): peer GPUs' gather buffers, written
     int32_t n_peers;               // straight from the kernel over NVLink (the all-gather fused into the epilogue)
-    int64_t peer_stride_k, peer_stride_pair;   // peer element (k, m) at (m >> 1)*stride_pair + k*stride_k + (m & 1)
+    int64_t peer_stride_k, peer_stride_pair, peer_stride_odd;   // peer element (k, m) at (m >> 1)*stride_pair + k*stride_k + (m & 1)*stride_odd
+    int32_t peer_multicast;        // 1: totals_peer[0] is an NVLink MULTICAST address (NVSwitch replicates one store to every GPU)
     void* forces_dec;
     uint8_t* mask_dec;
     int32_t forces_every;
@@ -75,6 +76,21 @@ struct K2Args {
     ScalD sd;
     ExpConsts ec;                // exp_neg_fast's constants (FP64 mode)
 };
+
+// One total into a peer GPU's gather buffer.  `mc`: the address is a multicast mapping (NVLS) -- one multimem.st leaves
+// this GPU and the NVSwitch delivers it to every GPU of the group, instead of one store per peer.
+__device__ __forceinline__ void peer_store(float* p, float v, int mc) {
+    if (mc) asm volatile("multimem.st.weak.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+    else *p = v;
+}
+__device__ __forceinline__ void peer_store(double* p, double v, int mc) {
+    if (mc) asm volatile("multimem.st.weak.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+    else *p = v;
+}
+__device__ __forceinline__ void peer_store2(float* p, float v0, float v1, int mc) {      // p 8-byte aligned
+    if (mc) asm volatile("multimem.st.weak.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v0), "f"(v1) : "memory");
+    else *(float2*)p = make_float2(v0, v1);
+}
 
 // U-wide vector of T in shared memory (one LDS/STS of 4*U or 8*U bytes)
 template <typename T, int U> struct alignas(sizeof(T) * U) VecU { T v[U]; };
@@ -631,8 +647,8 @@ __device__ __forceinline__ void k2_body(const K2Args& a) {
                     totals[o] = v;
                     if (a.n_peers > 0) {                               // peer GPUs (NVLink stores)
                         const int64_t mg = m0 + g;
-                        const int64_t op = (mg >> 1) * a.peer_stride_pair + krow * a.peer_stride_k + (mg & 1);
-                        for (int pr = 0; pr < a.n_peers; ++pr) ((T*)a.totals_peer[pr])[op] = v;
+                        const int64_t op = (mg >> 1) * a.peer_stride_pair + krow * a.peer_stride_k + (mg & 1) * a.peer_stride_odd;
+                        for (int pr = 0; pr < a.n_peers; ++pr) peer_store((T*)a.totals_peer[pr] + op, v, a.peer_multicast);
                     }
                 }
             }

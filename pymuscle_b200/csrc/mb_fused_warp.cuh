@@ -206,14 +206,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MB_W_MINB) k2w_f32(const 
                     // the same totals into the peer GPUs' gather buffers.  With the pair-major layout
                     // (stride_k == 2) the 32 lanes of the warp write 256 contiguous bytes per tile
                     const int64_t op = (m0 >> 1) * a.peer_stride_pair + krow * a.peer_stride_k;
-                    const bool vec = two && (((a.peer_stride_pair | a.peer_stride_k) & 1) == 0);
+                    const bool vec = two && a.peer_stride_odd == 1 && (((a.peer_stride_pair | a.peer_stride_k) & 1) == 0);
                     for (int pr = 0; pr < a.n_peers; ++pr) {
                         float* tp = (float*)a.totals_peer[pr] + op;
                         if (vec) {
-                            *(float2*)tp = make_float2(t0, t1);
+                            peer_store2(tp, t0, t1, a.peer_multicast);
                         } else {
-                            tp[0] = t0;
-                            if (two) tp[1] = t1;
+                            peer_store(tp, t0, a.peer_multicast);
+                            if (two) peer_store(tp + a.peer_stride_odd, t1, a.peer_multicast);
                         }
                     }
                 }
@@ -366,8 +366,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (FIB == MB_FIBERS_PYMUSCL
                 const int64_t o = krow * a.totals_stride_k + m;
                 ((float*)a.totals)[o] = v;
                 if (a.n_peers > 0) {
-                    const int64_t op = (m >> 1) * a.peer_stride_pair + krow * a.peer_stride_k + (m & 1);
-                    for (int pr = 0; pr < a.n_peers; ++pr) ((float*)a.totals_peer[pr])[op] = v;
+                    const int64_t op = (m >> 1) * a.peer_stride_pair + krow * a.peer_stride_k + (m & 1) * a.peer_stride_odd;
+                    for (int pr = 0; pr < a.n_peers; ++pr) peer_store((float*)a.totals_peer[pr] + op, v, a.peer_multicast);
                 }
             }
         }

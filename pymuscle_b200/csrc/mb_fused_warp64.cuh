@@ -242,8 +242,8 @@ k2w_f64(const K2Args a) {
             MB_ASSERT(krow < (a.K + a.totals_every - 1) / a.totals_every);
             ((double*)a.totals)[krow * a.totals_stride_k + m] = v;
             if (a.n_peers > 0) {                                                  // peer GPUs' gather buffers (NVLink stores)
-                const int64_t op = (m >> 1) * a.peer_stride_pair + krow * a.peer_stride_k + (m & 1);
-                for (int pr = 0; pr < a.n_peers; ++pr) ((double*)a.totals_peer[pr])[op] = v;
+                const int64_t op = (m >> 1) * a.peer_stride_pair + krow * a.peer_stride_k + (m & 1) * a.peer_stride_odd;
+                for (int pr = 0; pr < a.n_peers; ++pr) peer_store((double*)a.totals_peer[pr] + op, v, a.peer_multicast);
             }
         }
         __syncwarp();

@@ -177,8 +177,8 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1) k2x_f32(const
                 const int64_t krow = kl / a.totals_every;
                 ((float*)a.totals)[krow * a.totals_stride_k + m] = v;
                 if (a.n_peers > 0) {
-                    const int64_t op = (m >> 1) * a.peer_stride_pair + krow * a.peer_stride_k + (m & 1);
-                    for (int pr = 0; pr < a.n_peers; ++pr) ((float*)a.totals_peer[pr])[op] = v;
+                    const int64_t op = (m >> 1) * a.peer_stride_pair + krow * a.peer_stride_k + (m & 1) * a.peer_stride_odd;
+                    for (int pr = 0; pr < a.n_peers; ++pr) peer_store((float*)a.totals_peer[pr] + op, v, a.peer_multicast);
                 }
             }
         }

@@ -912,6 +912,9 @@ extern "C" int mb_step_fused_ex(const MbConfig* cfg, const void* params_dev, con
     a.n_peers = n_peers;
     a.peer_stride_k = w->peer_stride_k;
     a.peer_stride_pair = w->peer_stride_pair;
+    a.peer_stride_odd = w->peer_stride_odd > 0 ? w->peer_stride_odd : 1;
+    a.peer_multicast = w->peer_multicast != 0;
+    if (a.peer_multicast && n_peers != 1) return fail(MB_EINVAL, "mb_step_fused_gather: a multicast gather takes exactly one (multicast) buffer");
     if (n_peers > 0 && (w->peer_stride_k <= 0 || w->peer_stride_pair <= 0)) return fail(MB_EINVAL, "mb_step_fused_gather: peer strides must be positive");
     for (int i = 0; i < n_peers; ++i) {
         if (!w->peer_totals_dev[i]) return fail(MB_EINVAL, "mb_step_fused_gather: peer buffer %d is NULL", i);

@@ -143,12 +143,15 @@ class ShardedMuscleBatch:
         return out
 
     # ---- gather fused into the kernel: peer stores over NVLink -------------------------------
-    # Gather buffer (identical layout on every rank): one region per SOURCE rank r, pair-major:
-    #   region_r[pair][k][2],  pair = local muscle >> 1,  k < max_steps
-    # so the 32 lanes of a warp (32 steps of one muscle pair) store 256 contiguous bytes per tile.
-    def enable_peer_gather(self, max_steps: int):
+    # Gather buffer (identical layout on every rank): one region per SOURCE rank r, laid out so that what one warp
+    # stores per 32-step tile is 256 contiguous bytes of NVLink traffic:
+    #   FP32 mode (one warp per muscle PAIR): pair-major    region_r[pair][k][2],  pair = local muscle >> 1, k < max_steps
+    #   FP64 mode (one warp per muscle):      muscle-major  region_r[muscle][k]    (2 * pairs muscle slots)
+    def enable_peer_gather(self, max_steps: int, multicast: Optional[bool] = None, layout: str = "auto"):
         """Collective.  Allocates two symmetric gather buffers per rank (double-buffered between
-        consecutive windows) and exchanges their mappings."""
+        consecutive windows) and exchanges their mappings.  ``multicast``: store through the NVLink multicast
+        mapping of the buffers (NVLS: one store per total leaves the GPU, the switch replicates it) instead of
+        one store per peer; None = use it when the platform offers it."""
         import torch.distributed._symmetric_memory as symm_mem
         if self.S != 1:
             raise ValueError("the fused gather covers uniform batches")
@@ -163,6 +166,13 @@ class ShardedMuscleBatch:
             t = symm_mem.empty(offs[-1], dtype=self.local.dtype, device=self.local.device)
             self._pg["buf"].append(t)
             self._pg["hdl"].append(symm_mem.rendezvous(t, group))
+        have_mc = all(int(getattr(h, "multicast_ptr", 0) or 0) != 0 for h in self._pg["hdl"])
+        if multicast and not have_mc:
+            raise RuntimeError("NVLink multicast is not available for this group")
+        self._pg["multicast"] = have_mc if multicast is None else bool(multicast)
+        if layout not in ("auto", "pair", "muscle"):
+            raise ValueError("layout must be 'auto', 'pair' or 'muscle'")
+        self._pg["layout"] = layout                             # "auto": muscle-major in FP64 mode, pair-major in FP32 mode
 
     def step_many_peer_gather(self, excitations: torch.Tensor, step_size: float,
                               global_input: Optional[bool] = None, dense: bool = True):
@@ -183,15 +193,28 @@ class ShardedMuscleBatch:
         buf, hdl = pg["buf"][b], pg["hdl"][b]
         esz = buf.element_size()
         off = pg["offs"][self.rank] * esz
-        peers = [hdl.get_buffer(r, (buf.numel(),), buf.dtype).data_ptr() + off
-                 for r in range(self.world) if r != self.rank]
+        mc = pg.get("multicast", False)
+        if mc:                                                  # one multicast address: the switch fans the stores out
+            peers = [int(hdl.multicast_ptr) + off]
+        else:
+            peers = [hdl.get_buffer(r, (buf.numel(),), buf.dtype).data_ptr() + off
+                     for r in range(self.world) if r != self.rank]
         local = torch.empty(K, self.n_muscles_local, dtype=buf.dtype, device=buf.device)
-        self.local.step_many_gather(e, step_size, local, peers, 2, 2 * ks)
+        muscle_major = pg.get("layout", "auto") == "muscle" or (pg.get("layout", "auto") == "auto" and buf.dtype == torch.float64)
+        if muscle_major:
+            self.local.step_many_gather(e, step_size, local, peers, 1, 2 * ks, ks, multicast=mc)
+        else:
+            self.local.step_many_gather(e, step_size, local, peers, 2, 2 * ks, 1, multicast=mc)
         hdl.barrier()                                           # every rank's stores have landed everywhere
         views = []
         for r in range(self.world):
             if r == self.rank:
                 views.append(local)
+                continue
+            if muscle_major:
+                reg = buf[pg["offs"][r]: pg["offs"][r + 1]].view(2 * pg["pairs"][r], ks)
+                v = reg[: self.sizes[r], :K].permute(1, 0)                        # [K, muscles_r], strided view
+                views.append(v.contiguous() if dense else v)
                 continue
             reg = buf[pg["offs"][r]: pg["offs"][r + 1]].view(pg["pairs"][r], ks, 2)
             views.append(reg[:, :K].permute(1, 0, 2).reshape(K, -1)[:, : self.sizes[r]] if dense

@@ -399,13 +399,15 @@ class MuscleBatch:
 
     # ---- K2 with the gather of totals fused into the kernel (multi-GPU) -----------------
     def step_many_gather(self, excitations: torch.Tensor, step_size: float, out: torch.Tensor,
-                         peer_ptrs: Sequence[int], peer_stride_k: int, peer_stride_pair: int) -> None:
+                         peer_ptrs: Sequence[int], peer_stride_k: int, peer_stride_pair: int,
+                         peer_stride_odd: int = 1, multicast: bool = False) -> None:
         """``step_many`` whose totals go to ``out`` [K, M] (local) AND to raw device addresses in
         every peer GPU's gather buffer (``peer_ptrs``, mapped through symmetric memory and already
         offset to this rank's region; element (k, m) at (m >> 1) * peer_stride_pair +
-        k * peer_stride_k + (m & 1)) -- the kernel stores each total to all of them, so the
-        all-gather rides on the kernel's own stores over NVLink.  Uniform batches only; the
-        caller synchronises the ranks afterwards."""
+        k * peer_stride_k + (m & 1) * peer_stride_odd) -- the kernel stores each total to all of
+        them, so the all-gather rides on the kernel's own stores over NVLink.  ``multicast=True``:
+        ``peer_ptrs`` is ONE NVLink multicast address and every total leaves this GPU once.  Uniform
+        batches only; the caller synchronises the ranks afterwards."""
         e = excitations.to(device=self.device, dtype=self.dtype).contiguous()
         M = self.n_muscles
         assert self.S == 1 and e.dim() == 2 and e.shape[1] == M, "fused gather needs a uniform batch and exc [K, M]"
@@ -413,11 +415,18 @@ class MuscleBatch:
         assert out.is_contiguous() and out.dtype == self.dtype and tuple(out.shape) == (K, M)
         forces_last = torch.empty_like(self._forces) if self.fresh_outputs else self._forces
         arr = (C.c_void_p * max(1, len(peer_ptrs)))(*[C.c_void_p(int(p)) for p in peer_ptrs])
+        w = nat.MbFusedArgs()
+        w.rows, w.L, w.S, w.K = self.rows, self.L, 1, K
+        w.exc_dev, w.exc_stride_k, w.exc_hold, w.totals_every = e.data_ptr(), M, 1, 1
+        w.cpf_dev, w.dur_dev = self.cpf.data_ptr(), self.dur.data_ptr()
+        w.totals_dev, w.totals_stride_k = out.data_ptr(), M
+        w.forces_last_dev = forces_last.data_ptr()
+        w.peer_totals_dev, w.n_peers = arr, len(peer_ptrs)
+        w.peer_stride_k, w.peer_stride_pair, w.peer_stride_odd = int(peer_stride_k), int(peer_stride_pair), int(peer_stride_odd)
+        w.peer_multicast = int(bool(multicast))
         with torch.cuda.device(self.device):
-            nat.check(nat.lib().mb_step_fused_gather(
-                C.byref(self.cfg), _ptr(self._params), M, self.L, K, _ptr(e), M, _ptr(self.cpf), _ptr(self.dur),
-                _ptr(out), M, arr, len(peer_ptrs), int(peer_stride_k), int(peer_stride_pair), _ptr(forces_last),
-                float(step_size), self._stream()))
+            nat.check(nat.lib().mb_step_fused_ex(C.byref(self.cfg), _ptr(self._params), C.byref(w), float(step_size),
+                                                 self._stream()))
         self.launches += 1
         self._forces = forces_last
 

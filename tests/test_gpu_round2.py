@@ -50,7 +50,7 @@ def _batch_for(kernel, M, dev):
     raise AssertionError(kernel)
 
 
-@pytest.mark.parametrize("layout", ["step_major", "pair_major"])
+@pytest.mark.parametrize("layout", ["step_major", "pair_major", "muscle_major"])
 @pytest.mark.parametrize("n_peers", [1, 3])
 @pytest.mark.parametrize("kernel", ["k2w_f32", "k2_fused_f32", "k2_fused_f64", "k2u_f32"])
 def test_fused_gather_into_local_peer_buffers(cuda_device, kernel, n_peers, layout):
@@ -75,12 +75,19 @@ def test_fused_gather_into_local_peer_buffers(cuda_device, kernel, n_peers, layo
         bufs = [torch.full((K, M_total), nan, dtype=b.dtype, device=cuda_device) for _ in range(n_peers)]
         ptrs = [t.data_ptr() + col0 * t.element_size() for t in bufs]
         sk, sp = M_total, 2
-    else:                                                          # region[pair][k][2]: (2, 2 * K_max)
+    elif layout == "pair_major":                                   # region[pair][k][2]: (2, 2 * K_max, 1)
         kmax = K + 3
         bufs = [torch.full((pairs, kmax, 2), nan, dtype=b.dtype, device=cuda_device) for _ in range(n_peers)]
         ptrs = [t.data_ptr() for t in bufs]
-        sk, sp = 2, 2 * kmax
-    b.step_many_gather(x, dt, local, ptrs, sk, sp)
+        sk, sp, so = 2, 2 * kmax, 1
+    else:                                                          # region[muscle][k]: (1, 2 * K_max, K_max)
+        kmax = K + 3
+        bufs = [torch.full((2 * pairs, kmax), nan, dtype=b.dtype, device=cuda_device) for _ in range(n_peers)]
+        ptrs = [t.data_ptr() for t in bufs]
+        sk, sp, so = 1, 2 * kmax, kmax
+    if layout == "step_major":
+        so = 1
+    b.step_many_gather(x, dt, local, ptrs, sk, sp, so)
     torch.cuda.synchronize()
     got = local.cpu().numpy()
     if oras is None:
@@ -95,12 +102,15 @@ def test_fused_gather_into_local_peer_buffers(cuda_device, kernel, n_peers, layo
         if layout == "step_major":
             assert np.array_equal(h[:, col0:col0 + M], got), "peer copy differs from the local totals"
             assert np.isnan(h[:, :col0]).all() and np.isnan(h[:, col0 + M:]).all(), "stores outside this rank's region"
-        else:
+        elif layout == "pair_major":
             dense = h[:, :K].transpose(1, 0, 2).reshape(K, -1)
             assert np.array_equal(dense[:, :M], got)
             assert np.isnan(h[:, K:]).all(), "stores beyond the window"
             if M & 1:
                 assert np.isnan(dense[:, M:]).all(), "the empty half of the last pair was written"
+        else:
+            assert np.array_equal(h[:M, :K].T, got)
+            assert np.isnan(h[:, K:]).all() and np.isnan(h[M:]).all(), "stores outside the muscles' rows"
 
 
 # --------------------------------------------------------------------------------------------------
