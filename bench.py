@@ -592,7 +592,7 @@ def run_config3(h, args, cpu):
     bpu = K1_BYTES_PER_UNIT_STEP["standard_" + args.precision]
     peak, src = measured_hbm_peak()
     ach = units * args.steps / sec * bpu / 1e9
-    kkey = f"k1_flat_{args.precision}_config3"
+    kkey = f"k1_stream_{args.precision}_config3_env"
     facts = profile_facts(kkey)
     line = {"metric": METRIC, "value": value, "unit": METRIC, "n_gpus": h.world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True,
@@ -650,7 +650,7 @@ def run_config4(h, args, cpu):
     value = h.world * unit_steps * steps / sec
     peak = lane_op_peak(h, "f64")
     ach = unit_steps * OPS_PER_UNIT_STEP["potvin"] * steps / sec / 1e12
-    facts = profile_facts("k2w_f64_config4")
+    facts = profile_facts("k2w_f64_config4")        # (the same kernel as config #2 in FP64 mode; captured on that shape)
     line = {"metric": METRIC, "value": value, "unit": METRIC, "n_gpus": h.world, "steps": steps, "warmup": 10,
             "ms_per_step": 1e3 * sec / steps, "higher_is_better": True, "scaling": "strong" if args.strong else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": dict(workload_config(args), gather=mode),
