@@ -185,7 +185,10 @@ k1_stream(const K1sArgs<T> a) {
     constexpr int R = kStreamRows;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int W = a.W, NS = a.NS;
-    const int rowp = W + 2;                               // stage row pitch in elements (shift + round-up slack)
+    // stage row pitch in elements (shift + round-up slack).  Compile-time -- the instantiation's widest tile, whatever W a
+    // launch uses -- so that the 8 rows' shared-memory offsets are immediates: with a run-time pitch every row's read
+    // cost three integer instructions in a kernel that is short of issue slots (ncu), not of shared memory
+    constexpr int rowp = (CENTRAL ? StreamTraits<T>::kMaxWCentral : StreamTraits<T>::kMaxW) + 2;
     const uint32_t bar0 = smem_u32(smem_raw);             // full[NS] | empty[NS]
     using P = typename StreamTraits<T>::P;
     constexpr int G = StreamTraits<T>::G;
