@@ -58,7 +58,7 @@ static int launch_k1f(MB_K1S_PARAMS, const typename StreamTraits<T>::S& sc) {
     a.W = W; a.NS = NS;
     fa.group_units = knobs().k1_flat_group > 0 ? knobs().k1_flat_group : 16 * W;
     const int threads = W + 32, ncw = W / 32;
-    const int stage_bytes = kStreamRows * (wcap + 2) * 8 * (central ? 2 : 1) + StreamTraits<T>::G * W * 16;   // compile-time row pitch
+    const int stage_bytes = kStreamRows * (sizeof(T) == 4 ? wcap + 2 : W + 2) * 8 * (central ? 2 : 1) + StreamTraits<T>::G * W * 16;   // compile-time row pitch
     const int smem = 128 + NS * stage_bytes + NS * kStreamRows * kFlatMaxSegs * (int)sizeof(T) +
                      2 * ncw * kFlatMaxSegs * kStreamRows * (fatigue ? 2 : 1) * (int)sizeof(T) + 8 +
                      S * 8 + (S + 1) * 4 + (kFlatMaxGroups + 1) * 4 + 16;

@@ -57,7 +57,7 @@ static int launch_k1s(MB_K1S_PARAMS, const typename StreamTraits<T>::S& sc) {
     if (wmax > wcap) wmax = wcap;
     if (W > wmax) W = wmax;
     if (W < 32) W = 32;
-    const int stage_bytes = kStreamRows * (wcap + 2) * 8 * (central ? 2 : 1) +                             // state rows (compile-time pitch)
+    const int stage_bytes = kStreamRows * (sizeof(T) == 4 ? wcap + 2 : W + 2) * 8 * (central ? 2 : 1) +                             // state rows (compile-time pitch)
                             StreamTraits<T>::G * W * 16 * (c.param_rows > 1 ? kStreamRows : 1) +         // + unit parameters
                             (in_per_unit ? kStreamRows * (W + 2 * (16 / (int)sizeof(T))) * (int)sizeof(T) : 0);   // + per-unit inputs
     int NS = knobs().k1_stages;

@@ -47,7 +47,7 @@ k1_flat(const K1fArgs<T> fa) {
     constexpr int NSG = kFlatMaxSegs;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int W = a.W, NS = a.NS, S = a.S;
-    constexpr int rowp = (CENTRAL ? StreamTraits<T>::kMaxWCentral : StreamTraits<T>::kMaxW) + 2;   // compile-time pitch (mb_stream.cuh)
+    const int rowp = stream_row_pitch<T, CENTRAL>(W);     // compile-time in FP32 mode (mb_stream.cuh)
     const uint32_t bar0 = smem_u32(smem_raw);             // full[NS] | empty[NS]
     using P = typename StreamTraits<T>::P;
     constexpr int G = StreamTraits<T>::G;

@@ -77,6 +77,17 @@ struct K2Args {
     ExpConsts ec;                // exp_neg_fast's constants (FP64 mode)
 };
 
+// Ragged layouts (rows of several muscles): the kernels that take one muscle per block / per warp address muscle
+// m = (row, segment) through this
+struct K2xArgs {
+    K2Args k;                      // M = rows * S muscles; n unused (per-muscle lengths come from seg_off)
+    int64_t L;                     // units per row
+    int64_t total_units;           // rows * L
+    int32_t S;
+    const int32_t* seg_off;        // [S + 1] or NULL (one muscle of L units per row)
+    const double* seg_div;         // [S] output divisors or NULL (k.sf.inv_out)
+};
+
 // One total into a peer GPU's gather buffer.  `mc`: the address is a multicast mapping (NVLS) -- one multimem.st leaves
 // this GPU and the NVSwitch delivers it to every GPU of the group, instead of one store per peer.
 __device__ __forceinline__ void peer_store(float* p, float v, int mc) {

@@ -254,31 +254,44 @@ constexpr int kUPitch = 34;      // row pitch of the float force tile (even: 64-
 
 __device__ __forceinline__ float2 P2(float a, float b) { return make_float2(a, b); }
 
-// (PyMuscle fibers with two pairs per lane need ~100 registers: two blocks per SM instead of three, no spills)
+// Ragged rows (round 2): the same kernel takes one muscle (row, segment) per warp of a ragged batch whose muscles have
+// at most 256 units (NPU <= 4 pairs per lane; pairs beyond a muscle's length are skipped by warp-uniform predicates) --
+// a hopper leg's 74 / 120 / 169 / 120 units -- where the block-per-muscle kernel would give a 74-unit muscle 256 threads.
+// (PyMuscle fibers with two or more pairs per lane need 100+ registers: two blocks per SM instead of three)
 template <int FIB, int CENTRAL, int NPU, bool FORCES>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, (FIB == MB_FIBERS_PYMUSCLE && NPU == 2) ? 2 : 3) k2u_f32(const K2Args a) {
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, ((FIB == MB_FIBERS_PYMUSCLE && NPU == 2) || NPU > 2) ? 2 : 3)
+k2u_f32(const K2xArgs xa) {
+    const K2Args& a = xa.k;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* ftw = (float*)smem_raw + warp * (kWTile * kUPitch + 2 * kWTile);     // [32][34]
     float* excw = ftw + kWTile * kUPitch;                                        // [2][32]
 
-    const int n = a.n;
-    const int64_t m = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
+    const int64_t m = (int64_t)blockIdx.x * kWarpsPerBlock + warp;              // muscle = (row, segment)
     if (m >= a.M) return;                                 // warps are independent: no barrier below
-    MB_ASSERT(n <= 64 * NPU);
+    const int64_t row = m / xa.S;
+    const int seg = (int)(m - row * xa.S);
+    const int off0 = xa.seg_off ? xa.seg_off[seg] : 0;
+    const int n = xa.seg_off ? xa.seg_off[seg + 1] - off0 : (int)xa.L;
+    const int64_t base = row * xa.L + off0;                // first state element of this muscle
+    const int npa = (n + 63) >> 6;                         // pairs per lane this muscle needs (warp-uniform)
+    MB_ASSERT(npa <= NPU && base + n <= xa.total_units);
     const int ntiles = (a.K + kWTile - 1) / kWTile;
     const float* exc = (const float*)a.exc;
     const PairScal sc = pair_scal(a);
-    const float inv_out = a.sf.inv_out;
-    const float4* table = (const float4*)a.params + m * a.param_stride;         // this muscle's own table
+    const float inv_out = xa.seg_div ? (float)(1.0 / xa.seg_div[seg]) : a.sf.inv_out;
+    // per-instance tables: this muscle's own table (uniform batches); else the row's shared table at the muscle's offset
+    const float4* table = (const float4*)a.params + (a.param_stride ? m * a.param_stride : off0);
+    const int64_t tabL = xa.L;
 
     PairParams<float2> pp[NPU];
     PairState st[NPU];
 #pragma unroll
     for (int i = 0; i < NPU; ++i) {
+        if (i >= npa) continue;
         const int u0 = lane + 64 * i, u1 = u0 + 32;
-        const UnitF a0 = load_unit(table, n, u0 < n ? u0 : 0);
-        const UnitF a1 = load_unit(table, n, u1 < n ? u1 : 0);
+        const UnitF a0 = load_unit(table, tabL, u0 < n ? u0 : 0);
+        const UnitF a1 = load_unit(table, tabL, u1 < n ? u1 : 0);
         const PairParams<float> q0 = pair_params(a0, a), q1 = pair_params(a1, a);
         const float inf = __int_as_float(0x7f800000);
         pp[i].crit = P2(u0 < n ? q0.crit : inf, u1 < n ? q1.crit : inf);         // idle slot: never recruited, force 0
@@ -287,10 +300,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (FIB == MB_FIBERS_PYMUSCL
         pp[i].ctA = P2(q0.ctA, q1.ctA);         pp[i].ctB = P2(q0.ctB, q1.ctB);
         pp[i].fatdt = P2(q0.fatdt, q1.fatdt);   pp[i].rdidt = P2(q0.rdidt, q1.rdidt);
         pp[i].ptf = P2(q0.ptf, q1.ptf);         pp[i].ptf_lo = P2(q0.ptf_lo, q1.ptf_lo);
-        pair_init(st[i], pp[i], 0, u0 < n ? a.cpf[m * n + u0] : unit_peak(a0),
-                  (CENTRAL && u0 < n) ? a.dur[m * n + u0] : 0.0, a.adk_d);
-        pair_init(st[i], pp[i], 1, u1 < n ? a.cpf[m * n + u1] : unit_peak(a1),
-                  (CENTRAL && u1 < n) ? a.dur[m * n + u1] : 0.0, a.adk_d);
+        pair_init(st[i], pp[i], 0, u0 < n ? a.cpf[base + u0] : unit_peak(a0),
+                  (CENTRAL && u0 < n) ? a.dur[base + u0] : 0.0, a.adk_d);
+        pair_init(st[i], pp[i], 1, u1 < n ? a.cpf[base + u1] : unit_peak(a1),
+                  (CENTRAL && u1 < n) ? a.dur[base + u1] : 0.0, a.adk_d);
     }
 
     // excitation of (tile, step = lane); 0 beyond the window.  exc_stride_k == 0: constant
@@ -308,33 +321,35 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (FIB == MB_FIBERS_PYMUSCL
         __syncwarp();
         if (tile + 1 < ntiles) e_next = fetch(tile + 1);
 #pragma unroll
-        for (int i = 0; i < NPU; ++i) pair_begin_tile<CENTRAL>(st[i], sc);
+        for (int i = 0; i < NPU; ++i)
+            if (i < npa) pair_begin_tile<CENTRAL>(st[i], sc);
 
         auto do_step = [&](int s, auto last_tag) {
             constexpr bool LAST = decltype(last_tag)::value;
             const float e = es[s];
-            float2 fsum;
+            float2 fsum = make_float2(0.0f, 0.0f);
             bool write_now = false;
             if (FORCES) write_now = ((k0 + s + 1) % a.forces_every) == 0;
 #pragma unroll
             for (int i = 0; i < NPU; ++i) {
+                if (i >= npa) continue;
                 bool oa, ob;
                 const float2 F = pair_step<FIB, CENTRAL>(st[i], pp[i], sc, make_float2(e, e), oa, ob);
                 fsum = (i == 0) ? F : __fadd2_rn(fsum, F);
                 if (FORCES || LAST) {
                     const int u0 = lane + 64 * i, u1 = u0 + 32;
                     if (FORCES && write_now) {
-                        const int64_t base = (int64_t)((k0 + s) / a.forces_every) * a.M * n + m * n;
+                        const int64_t fb = (int64_t)((k0 + s) / a.forces_every) * xa.total_units + base;   // [record][rows][L]
                         float* fd = (float*)a.forces_dec;
-                        if (u0 < n) fd[base + u0] = F.x;
-                        if (u1 < n) fd[base + u1] = F.y;
+                        if (u0 < n) fd[fb + u0] = F.x;
+                        if (u1 < n) fd[fb + u1] = F.y;
                         if (a.mask_dec) {
-                            if (u0 < n) a.mask_dec[base + u0] = oa ? 1 : 0;
-                            if (u1 < n) a.mask_dec[base + u1] = ob ? 1 : 0;
+                            if (u0 < n) a.mask_dec[fb + u0] = oa ? 1 : 0;
+                            if (u1 < n) a.mask_dec[fb + u1] = ob ? 1 : 0;
                         }
                     }
                     if (LAST) {
-                        float* fl = (float*)a.forces_last + m * n;
+                        float* fl = (float*)a.forces_last + base;
                         if (u0 < n) fl[u0] = F.x;
                         if (u1 < n) fl[u1] = F.y;
                     }
@@ -347,7 +362,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (FIB == MB_FIBERS_PYMUSCL
         for (int s = 0; s < fast_steps; ++s) do_step(s, std::false_type{});
         if (has_last) do_step(steps - 1, std::true_type{});
 #pragma unroll
-        for (int i = 0; i < NPU; ++i) pair_renormalise<FIB>(st[i], pp[i]);
+        for (int i = 0; i < NPU; ++i)
+            if (i < npa) pair_renormalise<FIB>(st[i], pp[i]);
         __syncwarp();
         // ---- lane s sums the 32 lanes' forces of step k0 + s -----------------------------------
         const int kl = k0 + lane;                             // the step whose total this lane writes
@@ -376,9 +392,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (FIB == MB_FIBERS_PYMUSCL
 
 #pragma unroll
     for (int i = 0; i < NPU; ++i) {
+        if (i >= npa) continue;
         const int u0 = lane + 64 * i, u1 = u0 + 32;
-        if (u0 < n) pair_store<CENTRAL != 0>(st[i], 0, a, m * n + u0);
-        if (u1 < n) pair_store<CENTRAL != 0>(st[i], 1, a, m * n + u1);
+        if (u0 < n) pair_store<CENTRAL != 0>(st[i], 0, a, base + u0);
+        if (u1 < n) pair_store<CENTRAL != 0>(st[i], 1, a, base + u1);
     }
 }
 

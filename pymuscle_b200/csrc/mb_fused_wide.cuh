@@ -27,14 +27,6 @@ namespace mb {
 constexpr int kXTile = 32;         // steps per tile
 constexpr int kXPitch = 34;        // row pitch of a warp's float force tile (even: 64-bit row reads, conflict free)
 
-struct K2xArgs {
-    K2Args k;                      // M = rows * S muscles; n unused (per-muscle lengths come from seg_off)
-    int64_t L;                     // units per row
-    int64_t total_units;           // rows * L
-    int32_t S;
-    const int32_t* seg_off;        // [S + 1] or NULL (one muscle of L units per row)
-    const double* seg_div;         // [S] output divisors or NULL (k.sf.inv_out)
-};
 
 template <int FIB, int CENTRAL, int NPU, bool FORCES, int THREADS>
 __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1) k2x_f32(const K2xArgs xa) {

@@ -34,6 +34,8 @@ struct Knobs {
     int fused_general;   // MB_FUSED_GENERAL=1  fused kernels keep every clamp of the reference
     int f64_block;       // MB_F64_BLOCK=1      FP64 mode: block kernel where it would pick the warp kernel
     int fused_persist;   // MB_FUSED_PERSIST    -1 auto (windows of <= 24 steps), 0 never, 1 always: persistent short-window warp kernel
+    int fused_units;     // MB_FUSED_UNITS      FP32 mode, 129..256 units, shared table: warp-per-muscle kernel instead of the block
+                         //                     kernel: -1 auto (without central fatigue), 0 never, 1 always
     int fused_wide;      // MB_FUSED_WIDE=1     FP32 mode, n > 128: block-per-muscle kernel where it would pick the block kernel
 };
 const Knobs& knobs();

@@ -22,7 +22,7 @@ int launch_k1f_f64(MB_K1S_PARAMS);
 int launch_k2_block_f32(const K2Args& a, const FusedGeom& g, int fib, int cen, bool forces, cudaStream_t st);
 int launch_k2_block_f64(const K2Args& a, const FusedGeom& g, int fib, int cen, bool forces, cudaStream_t st);
 int launch_k2w_f32(const K2Args& a, const FusedGeom& g, int fib, int cen, bool forces, cudaStream_t st);
-int launch_k2u_f32(const K2Args& a, const FusedGeom& g, int fib, int cen, bool forces, cudaStream_t st);
+int launch_k2u_f32(const K2xArgs& xa, const FusedGeom& g, int fib, int cen, bool forces, cudaStream_t st);
 int launch_k2w_f64(const K2Args& a, const FusedGeom& g, int fib, int cen, bool forces, cudaStream_t st);
 int launch_k2x_f32(const K2xArgs& xa, const FusedGeom& g, int fib, int cen, bool forces, cudaStream_t st);
 

@@ -81,6 +81,12 @@ __device__ __forceinline__ float hill_gain(float rest, float cur, float prev, do
     return fl * ((float)ecc - (float)ecc / (1.0f + e));
 }
 
+// stage row pitch in elements: compile-time (the instantiation's widest tile) in FP32 mode, W + 2 in FP64 mode
+template <typename T, bool CENTRAL>
+__host__ __device__ __forceinline__ constexpr int stream_row_pitch(int W) {
+    return sizeof(T) == 4 ? (CENTRAL ? StreamTraits<T>::kMaxWCentral : StreamTraits<T>::kMaxW) + 2 : W + 2;
+}
+
 template <typename T>
 struct K1sArgs {
     const typename StreamTraits<T>::P* params;
@@ -188,7 +194,9 @@ k1_stream(const K1sArgs<T> a) {
     // stage row pitch in elements (shift + round-up slack).  Compile-time -- the instantiation's widest tile, whatever W a
     // launch uses -- so that the 8 rows' shared-memory offsets are immediates: with a run-time pitch every row's read
     // cost three integer instructions in a kernel that is short of issue slots (ncu), not of shared memory
-    constexpr int rowp = (CENTRAL ? StreamTraits<T>::kMaxWCentral : StreamTraits<T>::kMaxW) + 2;
+    // (FP32 mode only: in FP64 mode the immediates let the compiler hoist more and the 128-register consumers spill:
+    //  config #5 in FP64 mode 580 -> 624 us)
+    const int rowp = stream_row_pitch<T, CENTRAL>(W);
     const uint32_t bar0 = smem_u32(smem_raw);             // full[NS] | empty[NS]
     using P = typename StreamTraits<T>::P;
     constexpr int G = StreamTraits<T>::G;

@@ -55,6 +55,7 @@ const Knobs& mb::knobs() {
         q.f64_block = env_int("MB_F64_BLOCK", 0);
         q.fused_wide = env_int("MB_FUSED_WIDE", 0);
         q.fused_persist = env_int("MB_FUSED_PERSIST", -1);
+        q.fused_units = env_int("MB_FUSED_UNITS", -1);
         return q;
     }();
     return k;
@@ -747,6 +748,7 @@ extern "C" int mb_peripheral_fatigue(const MbConfig* cfg, const void* params_dev
 }
 
 // ---- fused geometry ---------------------------------------------------------------------
+static const int kWarpUnitsMax = 256;      // warp-per-muscle kernel (k2u_f32): 4 pairs of units per lane
 static const int kFusedMaxUnits = 480;     // threads per block <= 480 (15 warps), 2 blocks per SM in FP32 mode
 static const int kWideMaxUnits = 4096;     // block-per-muscle kernel: 512 threads x 4 pairs of units
 
@@ -760,8 +762,12 @@ static int fused_geometry(const MbConfig& c, int64_t M, int32_t n, int32_t K, in
     g->kernel = FK_BLOCK;
     const bool per_row = c.param_rows > 1;
     if (per_row && c.param_rows != M) return fail(MB_EINVAL, "per-instance tables need param_rows == M");
-    if (f32 && per_row && n <= 128) {
-        // per-instance tables: one warp per muscle, pairs of units
+    // shared tables, 129..256 units: the warp-per-muscle kernel beats the block kernel without central fatigue (measured:
+    // StandardMuscle n = 169 1.14e12 vs 9.2e11, n = 256 1.28e12 vs 1.20e12; Potvin n = 200 with its adaptation state: equal)
+    const bool units_mid = f32 && !per_row && upt == 0 && n > 128 && n <= kWarpUnitsMax &&
+                           (knobs().fused_units > 0 || (knobs().fused_units < 0 && !c.central_fatigue));
+    if (f32 && ((per_row && n <= 128) || units_mid)) {
+        // one warp per muscle, pairs of units: per-instance tables, and mid-sized muscles
         g->kernel = FK_WARP_UNITS;
         g->U = 1; g->q = kWarpsPerBlock; g->G = kWarpsPerBlock; g->Gp = g->G; g->T = kWTile;
         g->ns = n; g->npg = 0; g->ptp = 0;
@@ -874,7 +880,15 @@ extern "C" int mb_step_fused_ex(const MbConfig* cfg, const void* params_dev, con
         return fail(MB_EUNSUPPORTED, "mb_step_fused: rows of several muscles need FP32 mode and muscles of at most %d units",
                     kWideMaxUnits);
     FusedGeom g;
-    if (wide) {
+    if (wide && S > 1 && maxn <= kWarpUnitsMax) {
+        // rows of SHORT muscles: one warp per muscle (k2u_f32's arrangement, pairs of units, up to 256 units)
+        g.kernel = FK_WARP_UNITS;
+        g.U = 1; g.q = kWarpsPerBlock; g.G = kWarpsPerBlock; g.Gp = g.G; g.T = kWTile;
+        g.ns = maxn; g.npg = 0; g.ptp = 0;
+        g.threads = kWarpsPerBlock * 32;
+        g.smem = kWarpsPerBlock * (kWTile * kUPitch + 2 * kWTile) * (int)sizeof(float);
+        g.blocks = (M + g.G - 1) / g.G;
+    } else if (wide) {
         if (cfg->param_rows > 1 && (S != 1 || cfg->param_rows != M)) return fail(MB_EINVAL, "per-instance tables need a uniform batch with param_rows == M");
         g.kernel = FK_WIDE;
         g.threads = maxn <= 2048 ? 256 : 512;
@@ -945,15 +959,14 @@ extern "C" int mb_step_fused_ex(const MbConfig* cfg, const void* params_dev, con
     const int fib = cfg->fibers_kind;
     const bool forces = w->forces_every > 0;
     cudaStream_t st = (cudaStream_t)stream;
-    if (g.kernel == FK_WIDE) {
+    if (g.kernel == FK_WIDE || g.kernel == FK_WARP_UNITS) {
         K2xArgs xa;
         xa.k = a;
         xa.L = w->L; xa.total_units = w->rows * w->L; xa.S = S;
         xa.seg_off = S > 1 ? w->seg_off_dev : nullptr;
         xa.seg_div = S > 1 ? w->seg_div_dev : nullptr;
-        return launch_k2x_f32(xa, g, fib, cen, forces, st);
+        return g.kernel == FK_WIDE ? launch_k2x_f32(xa, g, fib, cen, forces, st) : launch_k2u_f32(xa, g, fib, cen, forces, st);
     }
-    if (g.kernel == FK_WARP_UNITS) return launch_k2u_f32(a, g, fib, cen, forces, st);
     if (g.kernel == FK_WARP_PAIR || g.kernel == FK_WARP_PAIR_PERSIST) return launch_k2w_f32(a, g, fib, cen, forces, st);
     if (f32) return launch_k2_block_f32(a, g, fib, cen, forces, st);
     // FP64: the fast path additionally needs the sigmoid's exponent bounded (no clamp in exp_neg_fast);
