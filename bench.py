@@ -489,11 +489,13 @@ def run_config2(h, args, cpu):
                     "d2h_bytes_per_step": d2h, "steps": e_steps, "ms_per_step": 1e3 * s / e_steps, "api": api}
 
         # headline: config #2 as stated -- constant excitation per muscle, totals sampled every `tev` steps
-        e2e = leg(lambda: batch.step_many_host(const_h, dt, out_dec, chunk=args.chunk, steps=K, totals_every=tev,
+        # (one sub-window per window: with 256 KB up and 26 MB down there is nothing to pipeline inside a window; the
+        #  download of window i overlaps the kernel of window i + 1)
+        e2e = leg(lambda: batch.step_many_host(const_h, dt, out_dec, chunk=K, steps=K, totals_every=tev,
                                                overlap_calls=True),
                   M * esz, out_dec.numel() * esz,
                   f"MuscleBatch.step_many_host(pinned exc[{M}] (constant over the window), dt, pinned totals[{K // tev},{M}], "
-                  f"steps={K}, totals_every={tev}, chunk={args.chunk}, overlap_calls=True): the excitation vector is uploaded and "
+                  f"steps={K}, totals_every={tev}, chunk={K}, overlap_calls=True): the excitation vector is uploaded and "
                   f"every {tev}-th step's totals are downloaded inside the timed region of every window")
         del out_dec
         variants = {}

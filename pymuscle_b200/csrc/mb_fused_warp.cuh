@@ -59,15 +59,16 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MB_W_MINB) k2w_f32(const 
     double* stage = (double*)((float2*)smem_raw + kWarpsPerBlock * kPerWarp) + (size_t)warp * 4 * ((n + 1) & ~1);
     const int stage_n = 2 * ((n + 1) & ~1);                                      // doubles per array in the stage
 
-    const int64_t npairs = (a.M + 1) >> 1;
-    const int64_t first = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
-    const int64_t stride = PERSIST ? (int64_t)gridDim.x * kWarpsPerBlock : npairs;   // (not PERSIST: exactly one pair per warp)
+    // (32-bit pair indices: the launcher takes batches of fewer than 2^31 muscles here; the persistent loop is short of
+    //  registers, and every 64-bit loop-carried value costs the step loop's schedule)
+    const int npairs = (int)((a.M + 1) >> 1);
+    const int first = (int)(blockIdx.x * kWarpsPerBlock + warp);
     if (first >= npairs) return;                          // warps are independent: no block barrier below
     const int ntiles = (a.K + kWTile - 1) / kWTile;
     const float* exc = (const float*)a.exc;
 
-    auto prefetch = [&](int64_t pair) {                   // state of `pair` -> this warp's stage (cp.async, one group)
-        const int64_t m0 = pair * 2;
+    auto prefetch = [&](int pair) {                       // state of `pair` -> this warp's stage (cp.async, one group)
+        const int64_t m0 = (int64_t)pair * 2;
         const int cnt = (m0 + 1 < a.M) ? 2 * n : n;       // units to fetch; m0 even => the source is 16-byte aligned
         const uint32_t sc = smem_u32(stage), sd = smem_u32(stage + stage_n);
         for (int i = lane; i < (cnt >> 1); i += 32) {
@@ -91,8 +92,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MB_W_MINB) k2w_f32(const 
         if (u >= n) core[i].disable();                                  // idle slot: never recruited, force 0
     }
 
-    for (int64_t pair = first; pair < npairs; pair += stride) {
-    const int64_t m0 = pair * 2;
+    auto run_pair = [&](const int pair) {
+    const int64_t m0 = (int64_t)pair * 2;
     const bool two = m0 + 1 < a.M;
     MB_ASSERT(m0 < a.M && (int64_t)(m0 + (two ? 2 : 1)) * n <= a.M * (int64_t)n);
     if (PERSIST) {
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MB_W_MINB) k2w_f32(const 
     }
     if (PERSIST) {
         __syncwarp();                                     // every lane has its state in registers: the stage is free
-        if (pair + stride < npairs) prefetch(pair + stride);
+        if (pair + (int)(gridDim.x * kWarpsPerBlock) < npairs) prefetch(pair + (int)(gridDim.x * kWarpsPerBlock));
     }
 
     // excitations of (tile, step = lane) for the two muscles; 0 beyond the window / batch
@@ -236,7 +237,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MB_W_MINB) k2w_f32(const 
             }
         }
     }
-    }   // pair loop
+    };   // run_pair
+    if constexpr (PERSIST) {
+        const int stride = (int)(gridDim.x * kWarpsPerBlock);
+        for (int pair = first; pair < npairs; pair += stride) run_pair(pair);
+    } else {
+        run_pair(first);                                  // exactly one pair per warp
+    }
 }
 
 // ======================================================================================

@@ -489,7 +489,7 @@ class MuscleBatch:
             with torch.cuda.device(self.device):
                 st = dict(chunk=chunk, hold=hold, tev=tev,
                           h2d=torch.cuda.Stream(self.device), d2h=torch.cuda.Stream(self.device),
-                          exc=[torch.empty(chunk // hold, M, dtype=self.dtype, device=self.device) for _ in range(2)],
+                          exc=None,                          # staging for per-step / held excitations: allocated on first use
                           tot=[torch.empty(chunk // tev, M, dtype=self.dtype, device=self.device) for _ in range(2)],
                           cexc=[torch.empty(M, dtype=self.dtype, device=self.device) for _ in range(2)],
                           up=[torch.cuda.Event() for _ in range(2)], run=[torch.cuda.Event() for _ in range(2)],
@@ -515,6 +515,9 @@ class MuscleBatch:
             b, c = i & 1, min(chunk, K - k0)
             ce_rows, ct_rows = (c + hold - 1) // hold, c // tev
             if not const:
+                if st["exc"] is None:
+                    with torch.cuda.device(self.device):
+                        st["exc"] = [torch.empty(chunk // hold, M, dtype=self.dtype, device=self.device) for _ in range(2)]
                 if i >= 2:
                     st["h2d"].wait_event(st["run"][b])       # the last kernel that read exc[b] is done
                 with torch.cuda.stream(st["h2d"]):

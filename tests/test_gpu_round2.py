@@ -403,10 +403,12 @@ def test_wide_muscle_10000_steps_fused(cuda_device):
     assert b.launches - launches0 == K // W, "a window of a 2,000-unit muscle must be one launch"
 
 
-@pytest.mark.parametrize("forces_n", [(9.0, 33.0, 21.0), (68.0, 824.0)])
+@pytest.mark.parametrize("forces_n", [(9.0, 33.0, 21.0), (20.0, 32.0, 45.0, 32.0), (68.0, 20.0), (68.0, 824.0), (68.0, 300.0)])
 def test_ragged_rows_fused_window(cuda_device, forces_n):
-    """Rows of several muscles (the arm model's layout) through the block-per-muscle kernel, with held controls and
-    decimated totals, against per-muscle oracles; (68 N, 824 N) = 256 and 3,127 units uses the 512-thread geometry."""
+    """Rows of several muscles in ONE fused launch, with held controls and decimated totals, against per-muscle oracles.
+    Short muscles run the warp-per-muscle kernel -- (20, 32, 45, 32 N) = a hopper leg's 74 / 120 / 169 / 120 units = 3 pairs per
+    lane, (68 N, 20 N) = 256 and 74 units = 4 pairs -- rows with a longer muscle the block-per-muscle kernel: (68 N, 300 N) =
+    256 and 1,137 units in 256-thread blocks, (68 N, 824 N) = 256 and 3,127 units in the 512-thread geometry."""
     specs = [MuscleSpec.standard(f) for f in forces_n]
     S, rows, K, dt, hold, tev = len(specs), 5, 96, 0.02, 4, 3
     b = MuscleBatch(specs, rows, cuda_device, "f32")
@@ -446,3 +448,36 @@ def test_wide_kernel_with_central_fatigue_and_potvin_fibers(cuda_device):
     close(got.cpu().numpy(), oracle_window(ora, exc, dt), "f32", float(ora.t.ptf.sum()), "totals")
     close(b.cpf.cpu().numpy(), ora.cpf, "f32", ora.t.ptf, "capacities")
     np.testing.assert_allclose(b.dur.cpu().numpy(), ora.dur, rtol=1e-9, atol=1e-12)
+
+
+def test_very_short_windows_use_the_persistent_prefetching_kernel(cuda_device):
+    """Windows of <= 24 steps on a batch larger than the resident warps run k2w_f32's persistent variant (cp.async prefetch of
+    the next muscle pair, direct state stores, red.add on the durations): against the oracle, over several windows, with an
+    odd muscle count and units that rest, fatigue and recover across window boundaries."""
+    n, M, K, dt = 40, 4801, 20, 0.02
+    sm = torch.cuda.get_device_properties(cuda_device).multi_processor_count
+    for kind in ("potvin", "standard"):
+        spec = MuscleSpec.potvin(n) if kind == "potvin" else MuscleSpec(n, fibers=MuscleSpec.standard().fibers,
+                                                                         pool=MuscleSpec.standard().pool,
+                                                                         input_scale=67.0, output_divisor=1.0)
+        b = MuscleBatch(spec, M, cuda_device, "f32")
+        if (M + 15) // 16 > 2 * sm:
+            assert b.fused_geometry(K)["blocks"] == 2 * sm, "expected the persistent geometry (resident blocks only)"
+        ora = OracleMuscles(n, M, kind)
+        if kind == "standard":
+            ora.max_arb_output = 1.0                                  # (a PyMuscle-fibers muscle with unit output divisor)
+        rng = np.random.default_rng(31)
+        level = rng.random(M)
+        for w in range(6):
+            gate = 0.0 if w in (2, 3) else 1.0                        # two windows at rest: recovery / untouched units
+            exc = (gate * level[None, :] * (0.8 + 0.2 * rng.random((K, M)))).astype(np.float32)
+            if kind == "potvin":
+                exc = exc * 67.0
+            got = b.step_many(torch.from_numpy(exc).to(cuda_device), dt)
+            want = oracle_window(ora, exc, dt)
+            close(got.cpu().numpy(), want, "f32", float(ora.t.ptf.sum()), f"{kind} totals, window {w}")
+            close(b.cpf.cpu().numpy(), ora.cpf, "f32", ora.t.ptf, f"{kind} capacities, window {w}")
+            np.testing.assert_allclose(b.dur.cpu().numpy(), ora.dur, rtol=1e-9, atol=1e-12)
+        if kind == "potvin":
+            untouched = ora.cpf == ora.t.ptf                          # never recruited: must keep the exact float64 peak
+            assert untouched.any() and np.array_equal(b.cpf.cpu().numpy()[untouched], ora.cpf[untouched])
