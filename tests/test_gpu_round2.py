@@ -481,3 +481,50 @@ def test_very_short_windows_use_the_persistent_prefetching_kernel(cuda_device):
         if kind == "potvin":
             untouched = ora.cpf == ora.t.ptf                          # never recruited: must keep the exact float64 peak
             assert untouched.any() and np.array_equal(b.cpf.cpu().numpy()[untouched], ora.cpf[untouched])
+
+
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_hopper_rows_3000_steps_single_and_fused(cuda_device, precision):
+    """A hopper leg's four muscles (74 / 120 / 169 / 120 units; examples/envs/muscled_hopper.py:10-23) over 3,000 steps with
+    bursts and rests: env steps through the flat-tiled streaming kernel (both modes) and, in FP32 mode, the same protocol as
+    fused windows through the warp-per-muscle kernel -- outputs, fatigue readout, capacities against per-muscle oracles at
+    the mode's tolerance."""
+    forces_n, rows, K, dt = (20.0, 32.0, 45.0, 32.0), 3, 3000, 0.02
+    specs = [MuscleSpec.standard(f) for f in forces_n]
+    S = len(specs)
+    rng = np.random.default_rng(41)
+    base = rng.random((rows, S))
+    gate = ((np.arange(K) // 400) % 3 != 2).astype(np.float64)          # 800 steps on, 400 at rest
+    act = (gate[:, None, None] * base[None] * (0.85 + 0.15 * rng.random((K, rows, S)))).astype(np.float32)
+    oras = [OracleMuscles.standard(f, m=rows) for f in forces_n]
+    want = np.empty((K, rows, S))
+    want_fat = np.empty((K, rows, S))
+    for k in range(K):
+        for i, o in enumerate(oras):
+            want[k, :, i] = o.step(act[k, :, i].astype(np.float64), dt).total
+            want_fat[k, :, i] = o.peripheral_fatigue()
+    ptf = np.concatenate([sp.tables()["ptf"] for sp in specs])
+    cpf_want = np.concatenate([o.cpf for o in oras], axis=1)
+
+    b = MuscleBatch(specs, rows, cuda_device, precision)
+    x = torch.from_numpy(act).to(cuda_device, b.dtype)
+    outs, fats = [], []
+    for k in range(K):
+        o, f = b.step_env(x[k], dt)
+        outs.append(o)
+        fats.append(f)
+    got = torch.stack(outs).double().cpu().numpy()
+    for i, sp in enumerate(specs):
+        close(got[:, :, i], want[:, :, i], precision, total_scale(sp), f"single-step totals, muscle {i}")
+    close(torch.stack(fats).cpu().numpy(), want_fat, precision, 1.0, "fatigue readout")
+    close(b.cpf.cpu().numpy(), cpf_want, precision, ptf, "capacities after 3,000 single steps")
+
+    if precision == "f32":
+        fb = MuscleBatch(specs, rows, cuda_device, "f32")
+        l0 = fb.launches
+        tot = torch.cat([fb.step_many(x[w:w + 500].reshape(500, rows * S), dt) for w in range(0, K, 500)])
+        assert fb.launches - l0 == K // 500, "a window of ragged rows must be one launch"
+        tot = tot.cpu().numpy().reshape(K, rows, S)
+        for i, sp in enumerate(specs):
+            close(tot[:, :, i], want[:, :, i], "f32", total_scale(sp), f"fused totals, muscle {i}")
+        close(fb.cpf.cpu().numpy(), cpf_want, "f32", ptf, "capacities after 3,000 fused steps")

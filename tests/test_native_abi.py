@@ -169,3 +169,30 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(nat, "LIB_PATH", "/nonexistent/libmuscle_b200.so")
     with pytest.raises(ImportError, match="no CPU fallback"):
         nat.lib()
+
+
+def test_header_is_plain_c_and_struct_layouts_match_the_ctypes_mirrors(tmp_path):
+    """include/muscle_b200.h compiles as C (gcc, no CUDA), and sizeof / offsetof of every struct that crosses the
+    boundary equal the ctypes mirrors in pymuscle_b200/_native.py."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    mirrors = {"MbConfig": nat.MbConfig, "MbHill": nat.MbHill, "MbFusedArgs": nat.MbFusedArgs}
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "muscle_b200.h"', "int main(void) {"]
+    for name, cls in mirrors.items():
+        lines.append(f'  printf("{name} %zu\\n", sizeof({name}));')
+        for field, _ in cls._fields_:
+            lines.append(f'  printf("{name}.{field} %zu\\n", offsetof({name}, {field}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
+                   check=True, capture_output=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for name, cls in mirrors.items():
+        assert int(out[name]) == C.sizeof(cls), name
+        for field, _ in cls._fields_:
+            assert int(out[f"{name}.{field}"]) == getattr(cls, field).offset, f"{name}.{field}"
