@@ -594,7 +594,7 @@ def run_config3(h, args, cpu):
     bpu = K1_BYTES_PER_UNIT_STEP["standard_" + args.precision]
     peak, src = measured_hbm_peak()
     ach = units * args.steps / sec * bpu / 1e9
-    kkey = f"k1_stream_{args.precision}_config3_env"
+    kkey = "k1_flat_f32_config3_env" if args.precision == "f32" else "k1_stream_f64_config3_env"
     facts = profile_facts(kkey)
     line = {"metric": METRIC, "value": value, "unit": METRIC, "n_gpus": h.world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True,
@@ -604,7 +604,7 @@ def run_config3(h, args, cpu):
                     "h2d_bytes_per_step": a_h[0].numel() * a_h[0].element_size(),
                     "d2h_bytes_per_step": o_h.numel() * o_h.element_size() + f_h.numel() * 8,
                     "api": "MuscleGroupEnv.step(actions from pinned host memory) -> outputs, fatigue copied to pinned host memory"},
-            "roofline": {"kernel": "single-step streaming kernel + fatigue epilogue", "bound": "hbm", "achieved": ach, "peak": peak,
+            "roofline": {"kernel": ("k1_flat<float>" if args.precision == "f32" else "k1_stream<double>") + " + fatigue epilogue", "bound": "hbm", "achieved": ach, "peak": peak,
                          "unit": "GB/s", "frac": ach / peak, "peak_source": src, "bytes_per_unit_step": bpu,
                          "traffic": facts["traffic"], "ncu": facts["pipes"]},
             "cpu_baseline": cpu}

@@ -32,6 +32,9 @@ constexpr int kFlatMaxSegs = 16;        // muscles per group (bounds the per-war
 constexpr int kFlatMaxGroups = 256;     // groups per row
 constexpr int kFlatMaxS = 1024;         // muscles per row the kernel takes (group table is built by one thread)
 
+__device__ __forceinline__ float fma_t(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ double fma_t(double a, double b, double c) { return fma(a, b, c); }
+
 template <typename T>
 struct K1fArgs {
     K1sArgs<T> s;                       // in_per_unit = 0, param_stride = 0, S > 1
@@ -103,7 +106,7 @@ k1_flat(const K1fArgs<T> fa) {
 
     if (warp == ncw) {
         // ------------------------------ producer warp ----------------------------------------
-        uint32_t it = 0;
+        uint32_t slot = 0, phase = 0;                     // ring position (it % NS, (it / NS) & 1 without the divisions)
         int64_t chunk = (int64_t)(blockIdx.x / (unsigned)ng);
         int grp = (int)(blockIdx.x % (unsigned)ng);
         // the item's inputs, 4 per lane: value j of lane l is (row, muscle) = ((l + 32 j) / NSG, (l + 32 j) % NSG)
@@ -128,8 +131,9 @@ k1_flat(const K1fArgs<T> fa) {
             const int64_t r0 = chunk * R;
             const int c0 = segoff_s[grp_s[grp]], c1 = segoff_s[grp_s[grp + 1]];
             const int nrows = (int)min((int64_t)R, a.rows - r0);
-            for (int u0 = c0; u0 < c1; u0 += W, ++it) {
-                const uint32_t s = it % NS, ph = (it / NS) & 1;
+            for (int u0 = c0; u0 < c1; u0 += W) {
+                const uint32_t s = slot, ph = phase;
+                if (++slot == (uint32_t)NS) { slot = 0; phase ^= 1u; }
                 mbar_wait(bar0 + 8u * (NS + s), ph ^ 1);  // stage free (passes at once in the first round)
                 const int count = min(W, c1 - u0);
                 const uint32_t pbytes = (uint32_t)count * 16u;
@@ -163,7 +167,7 @@ k1_flat(const K1fArgs<T> fa) {
     }
 
     // ---------------------------------- consumer warps ----------------------------------------
-    uint32_t it = 0, item_no = 0;
+    uint32_t slot = 0, phase = 0, item_no = 0;            // ring position as counters: NS is a run-time value
     int64_t chunk = (int64_t)(blockIdx.x / (unsigned)ng);
     int grp = (int)(blockIdx.x % (unsigned)ng);
     const int rr = (lane >> 2) & 7;                       // the row whose warp total this lane holds after a butterfly
@@ -184,6 +188,12 @@ k1_flat(const K1fArgs<T> fa) {
 #pragma unroll
         for (int r = 0; r < R; ++r) { partial[r] = 0; csum[r] = 0; }
         int wseg = -1;                                    // the muscle this warp's registers are accumulating (-1: none)
+        // Clearing the accumulators is folded into the first accumulation after a flush: acc = acc * keep + F with keep = 0
+        // (an FMA in place of the add).  As a conditional assignment the clear made the compiler merge 16 registers on
+        // both sides of the branch -- 32 moves per tile in a kernel that is short of issue slots
+        // (FP32 mode only: in FP64 mode the extra live value costs the 128-register consumers spills)
+        constexpr bool kFoldClear = sizeof(T) == 4;
+        T keep = T(1);
         int seg = sg0;                                    // muscle of this thread's column (advances monotonically)
         // registers -> this warp's slots of local muscle sl; `mine`: the lanes whose column belongs to that muscle
         auto flush_masked = [&](int sl, bool mine) {
@@ -205,8 +215,9 @@ k1_flat(const K1fArgs<T> fa) {
 #pragma unroll
             for (int r = 0; r < R; ++r) { partial[r] = 0; csum[r] = 0; }
         };
-        for (int u0 = c0; u0 < c1; u0 += W, ++it) {
-            const uint32_t s = it % NS, ph = (it / NS) & 1;
+        for (int u0 = c0; u0 < c1; u0 += W) {
+            const uint32_t s = slot, ph = phase;
+            if (++slot == (uint32_t)NS) { slot = 0; phase ^= 1u; }
             const int c = u0 + tid;
             const bool active = c < c1;
             const int cc = active ? c : c1 - 1;           // idle lanes shadow the group's last column (their forces are 0)
@@ -215,7 +226,7 @@ k1_flat(const K1fArgs<T> fa) {
             const int seg_lo = __shfl_sync(0xffffffffu, seg, 0), seg_hi = __shfl_sync(0xffffffffu, seg, 31);
             if (wseg >= 0 && (seg_lo != wseg || seg_hi != wseg)) {      // the warp leaves its muscle: flush first
                 flush_masked(wseg - sg0, true);
-                clear();
+                if constexpr (kFoldClear) keep = T(0); else clear();
                 wseg = -1;
             }
             mbar_wait(bar0 + 8u * s, ph);
@@ -233,31 +244,48 @@ k1_flat(const K1fArgs<T> fa) {
                 T* fp = FORCES ? a.forces + i0 : nullptr;
                 double* cp = a.cpf + i0;
                 double* dp = CENTRAL ? a.dur + i0 : nullptr;
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    if (nrows == R || r < nrows) {
-                        const int sh = (r & 1) ? sh1 : sh0;
-                        const double cv = cs[r * rowp + sh], dv = CENTRAL ? ds[r * rowp + sh] : 0.0;
-                        double cn, dn = dv;
-                        const T F = k1s_unit<CENTRAL, RECOVERY>(a, p, xs[r * NSG], cv, dv, fatdt, rdidt, ptf, cn, dn, exp2_tab);
-                        if (FORCES) *fp = F;
-                        *cp = cn;
-                        if (CENTRAL) *dp = dn;
+                auto row = [&](int r) {
+                    const int sh = (r & 1) ? sh1 : sh0;
+                    const double cv = cs[r * rowp + sh], dv = CENTRAL ? ds[r * rowp + sh] : 0.0;
+                    double cn, dn = dv;
+                    const T F = k1s_unit<CENTRAL, RECOVERY>(a, p, xs[r * NSG], cv, dv, fatdt, rdidt, ptf, cn, dn, exp2_tab);
+                    if (FORCES) fp[(int64_t)r * a.L] = F;
+                    cp[(int64_t)r * a.L] = cn;
+                    if (CENTRAL) dp[(int64_t)r * a.L] = dn;
+                    if constexpr (kFoldClear) {
+                        partial[r] = fma_t(partial[r], keep, F);
+                        if (FATIGUE) csum[r] = fma_t(csum[r], keep, (T)(ptf - cn));
+                    } else {
                         partial[r] += F;
                         if (FATIGUE) csum[r] += (T)(ptf - cn);
                     }
-                    if (FORCES) fp += a.L;
-                    cp += a.L;
-                    if (CENTRAL) dp += a.L;
+                };
+                if (nrows == R) {                                 // full chunk: straight-line code for the 8 rows
+#pragma unroll
+                    for (int r = 0; r < R; ++r) row(r);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        if (r < nrows) {
+                            row(r);
+                        } else if (kFoldClear) {
+                            partial[r] *= keep;
+                            csum[r] *= keep;
+                        }
+                    }
                 }
+            } else if (kFoldClear) {                              // idle lanes of a group's last tile
+#pragma unroll
+                for (int r = 0; r < R; ++r) { partial[r] *= keep; csum[r] *= keep; }
             }
+            keep = T(1);
             __syncwarp();
             if (lane == 0) mbar_arrive(bar0 + 8u * (NS + s));    // this warp is done with the stage
             if (seg_lo == seg_hi) {                               // the whole warp inside one muscle: keep summing in registers
                 wseg = seg_lo;
             } else {                                              // the warp straddles muscle boundaries: one masked reduction each
                 for (int sq = seg_lo; sq <= seg_hi; ++sq) flush_masked(sq - sg0, active && seg == sq);
-                clear();
+                if constexpr (kFoldClear) keep = T(0); else clear();
             }
         }
         if (wseg >= 0) flush_masked(wseg - sg0, true);

@@ -244,7 +244,7 @@ k1_stream(const K1sArgs<T> a) {
 
     if (warp == ncw) {
         // ------------------------------ producer warp ----------------------------------------
-        uint32_t it = 0;
+        uint32_t slot = 0, phase = 0;                     // ring position (it % NS, (it / NS) & 1 without the divisions)
         int64_t chunk = (int64_t)(blockIdx.x / (unsigned)a.S);
         int seg = (int)(blockIdx.x % (unsigned)a.S);
         for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
@@ -252,8 +252,9 @@ k1_stream(const K1sArgs<T> a) {
             const int off0 = seg_off ? seg_off[seg] : 0;
             const int n = seg_off ? seg_off[seg + 1] - off0 : (int)a.L;
             const int nrows = (int)min((int64_t)R, a.rows - r0);
-            for (int u0 = 0; u0 < n; u0 += W, ++it) {
-                const uint32_t s = it % NS, ph = (it / NS) & 1;
+            for (int u0 = 0; u0 < n; u0 += W) {
+                const uint32_t s = slot, ph = phase;
+                if (++slot == (uint32_t)NS) { slot = 0; phase ^= 1u; }
                 mbar_wait(bar0 + 8u * (NS + s), ph ^ 1);  // stage free (passes at once in the first round)
                 const int count = min(W, n - u0);
                 const int64_t e0 = off0 + u0;             // element offset inside a row
@@ -313,7 +314,7 @@ k1_stream(const K1sArgs<T> a) {
         for (int r = 0; r < R; ++r)
             x[r] = (!a.in_per_unit && r0 + r < a.rows) ? a.in[(r0 + r) * a.S + seg] : T(0);
     };
-    uint32_t it = 0, item_no = 0;
+    uint32_t slot = 0, phase = 0, item_no = 0;            // ring position as counters: NS is a run-time value
     T xnext[R];
     int64_t chunk_next = (int64_t)(blockIdx.x / (unsigned)a.S);
     int seg_next = (int)(blockIdx.x % (unsigned)a.S);
@@ -338,8 +339,9 @@ k1_stream(const K1sArgs<T> a) {
         }
         constexpr bool want_fatigue = FATIGUE;                // fused get_peripheral_fatigue epilogue
         fetch_inputs(chunk_next, seg_next, xnext);                // (rows past the end read as 0)
-        for (int u0 = 0; u0 < n; u0 += W, ++it) {
-            const uint32_t s = it % NS, ph = (it / NS) & 1;
+        for (int u0 = 0; u0 < n; u0 += W) {
+            const uint32_t s = slot, ph = phase;
+            if (++slot == (uint32_t)NS) { slot = 0; phase ^= 1u; }
             const int u = u0 + tid;
             const bool active = u < n;
             // first wanted element of a staged row: r0 * L is even (r0 is a multiple of 8), so row r starts

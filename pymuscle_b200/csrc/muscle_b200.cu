@@ -631,13 +631,14 @@ static bool k1s_eligible(const MbConfig& c, int64_t L, int32_t stage, int32_t in
 }
 
 // Rows of several muscles with one input per muscle: the flat-tiled kernel (mb_flat.cuh)
-// Measured on B200 (scripts/r2_ragged.py): flat tiling wins where muscles are short against a tile (hopper legs: +38 % FP32,
-// +48 % FP64; 8 x 256 units: +4..10 % FP32) and loses a few per cent where every muscle fills several tiles anyway.
+// Measured on B200 (scripts/r2_ragged.py, % of HBM peak, k1_stream -> k1_flat).  FP32 mode: flat tiling wins on every
+// ragged layout but one -- hopper legs 50 -> 77 % (env step 45 -> 64 %), 8 x 256 units 91 -> 94 % (72 -> 89 %), the arm
+// 81 -> 85 % (79 -> 84 %), 30 x 1,137 units 89.5 -> 87.5 % (84.9 -> 85.5 %) -- so it takes all of them.  FP64 mode: only
+// where muscles are short against a tile (hopper 36 -> 51 %); with muscles of several tiles k1_stream's grouped rows win.
 static bool use_flat(const MbConfig& c, int64_t L, int32_t S, int32_t in_per_unit) {
     if (!(S > 1 && S <= kFlatMaxS && !in_per_unit && c.param_rows <= 1) || knobs().k1_flat == 0) return false;
-    if (knobs().k1_flat > 0) return true;
-    const int64_t mean_n = L / S;
-    return mean_n <= (c.precision == MB_F32 ? 512 : 192);
+    if (knobs().k1_flat > 0 || c.precision == MB_F32) return true;
+    return L / S <= 192;
 }
 
 extern "C" int mb_step(const MbConfig* cfg, const void* params_dev, int64_t rows, int64_t L, int32_t S,

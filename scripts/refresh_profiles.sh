@@ -10,7 +10,9 @@ cp $O/prof_k2w_f32_summary.txt $P/${R}_k2w_f32_config2_ncu_full_summary.txt
 cp $O/prof_k2w_f64_summary.txt $P/${R}_k2w_f64_config2_ncu_full_summary.txt
 cp $O/prof_k1_summary.txt $P/${R}_k1_stream_f32_config5_ncu_full_summary.txt
 cp $O/prof_k1_f64_summary.txt $P/${R}_k1_stream_f64_config5_ncu_full_summary.txt
-cp $O/prof_env_summary.txt $P/${R}_k1_stream_f32_config3_env_ncu_full_summary.txt
+cp $O/prof_env_summary.txt $P/${R}_k1_flat_f32_config3_env_ncu_full_summary.txt
+cp $O/prof_hopper_summary.txt $P/${R}_k1_flat_f32_hopper_env_ncu_full_summary.txt
+rm -f $P/${R}_k1_stream_f32_config3_env_ncu_full_summary.txt
 cp $O/prof_wide_summary.txt $P/${R}_k2x_f32_n2000_ncu_full_summary.txt
 cat $O/sweeps.txt > $P/${R}_sweeps_one_gpu.txt
 { echo "== scripts/r2_wide.py =="; cat $O/wide.txt; echo; echo "== scripts/r2_ragged.py =="; cat $O/ragged.txt; echo; echo "== scripts/perf_env_small.py =="; cat $O/env_small.txt; echo; echo "== scripts/perf_dropin.py =="; cat $O/dropin.txt; } > $P/${R}_kernels_one_gpu.txt
@@ -45,7 +47,8 @@ for key, f in (("k2w_f32_config2", "profiles/r2_k2w_f32_config2_ncu_full_summary
                ("k2w_f64_config4", "profiles/r2_k2w_f64_config2_ncu_full_summary.txt"),
                ("k1_stream_f32_config5", "profiles/r2_k1_stream_f32_config5_ncu_full_summary.txt"),
                ("k1_stream_f64_config5", "profiles/r2_k1_stream_f64_config5_ncu_full_summary.txt"),
-               ("k1_stream_f32_config3_env", "profiles/r2_k1_stream_f32_config3_env_ncu_full_summary.txt"),
+               ("k1_flat_f32_config3_env", "profiles/r2_k1_flat_f32_config3_env_ncu_full_summary.txt"),
+               ("k1_flat_f32_hopper_env", "profiles/r2_k1_flat_f32_hopper_env_ncu_full_summary.txt"),
                ("k2x_f32_n2000", "profiles/r2_k2x_f32_n2000_ncu_full_summary.txt")):
     try:
         traffic[key], pipes[key] = grab(f)

@@ -37,6 +37,7 @@ cap prof_k2w_f32 k2w_f32 scripts/prof_fused.py f32 65536
 cap prof_k2w_f64 k2w_f64 scripts/prof_fused.py f64 32768
 cap prof_k1 k1_stream scripts/prof_single.py f32
 cap prof_k1_f64 k1_stream scripts/prof_single.py f64 65536
-cap prof_env k1_stream scripts/prof_env.py f32
+cap prof_env k1_flat scripts/prof_env.py f32
+cap prof_hopper k1_flat scripts/prof_hopper.py f32
 cap prof_wide k2x_f32 scripts/prof_wide.py
 cat $O/bench.json
