@@ -687,6 +687,7 @@ __device__ __forceinline__ void k2_body(const K2Args& a) {
         }
         if (has_unit) {
             core.begin_tile();
+            int fphase = FORCES ? k0 % a.forces_every : 0;        // steps since the last captured one
             const T* es = es0 + slot * a.T * a.Gp;
             V* fp = fwr;
 #pragma unroll 2
@@ -698,7 +699,8 @@ __device__ __forceinline__ void k2_body(const K2Args& a) {
                 *fp = fv;
                 if (FORCES) {
                     const int k = k0 + s;
-                    if (((k + 1) % a.forces_every) == 0) {
+                    if (++fphase == a.forces_every) {             // every forces_every-th step, counted instead of k % f
+                        fphase = 0;
                         const int64_t dec_base = (int64_t)(k / a.forces_every) * a.M * n;
 #pragma unroll
                         for (int j = 0; j < U; ++j) {

@@ -143,12 +143,16 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MB_W_MINB) k2w_f32(const 
         for (int i = 0; i < UPL; ++i) core[i].begin_tile();
 
         // one step of the warp's two muscles; LAST = the window's final step (current_forces wanted)
+        int fphase = FORCES ? k0 % a.forces_every : 0;        // steps since the last captured one
         auto do_step = [&](int s, auto last_tag) {
             constexpr bool LAST = decltype(last_tag)::value;
             const float2 e = es[s];
             float2 fsum;
             bool write_now = false;
-            if (FORCES) write_now = ((k0 + s + 1) % a.forces_every) == 0;
+            if (FORCES) {                                     // every forces_every-th step, counted (a per-step modulo is ~20 instructions)
+                write_now = ++fphase == a.forces_every;
+                if (write_now) fphase = 0;
+            }
 #pragma unroll
             for (int i = 0; i < UPL; ++i) {
                 bool oa, ob;
@@ -331,12 +335,16 @@ k2u_f32(const K2xArgs xa) {
         for (int i = 0; i < NPU; ++i)
             if (i < npa) pair_begin_tile<CENTRAL>(st[i], sc);
 
+        int fphase = FORCES ? k0 % a.forces_every : 0;        // steps since the last captured one
         auto do_step = [&](int s, auto last_tag) {
             constexpr bool LAST = decltype(last_tag)::value;
             const float e = es[s];
             float2 fsum = make_float2(0.0f, 0.0f);
             bool write_now = false;
-            if (FORCES) write_now = ((k0 + s + 1) % a.forces_every) == 0;
+            if (FORCES) {                                     // every forces_every-th step, counted (a per-step modulo is ~20 instructions)
+                write_now = ++fphase == a.forces_every;
+                if (write_now) fphase = 0;
+            }
 #pragma unroll
             for (int i = 0; i < NPU; ++i) {
                 if (i >= npa) continue;

@@ -105,6 +105,7 @@ k2w_f64(const K2Args a) {
             for (int i = 0; i < UPL; ++i) G[i] = -expm1(dur[i] * sc.mitau);
         }
 
+        int fphase = FORCES ? k0 % a.forces_every : 0;        // steps since the last captured one
         auto do_step = [&](int s, auto last_tag) {
             constexpr bool LAST = decltype(last_tag)::value;
             const double e = __dmul_rn(es[s], sc.input_scale);                    // muscle.py:275, once per muscle-step
@@ -130,7 +131,10 @@ k2w_f64(const K2Args a) {
             const int kon = UPL;
 #endif
             bool write_now = false;
-            if (FORCES) write_now = ((k0 + s + 1) % a.forces_every) == 0;
+            if (FORCES) {                                     // every forces_every-th step, counted (a per-step modulo is ~20 instructions)
+                write_now = ++fphase == a.forces_every;
+                if (write_now) fphase = 0;
+            }
             auto emit = [&](int i, double F, bool oni) {                        // per-unit outputs of the FORCES / LAST variants
                 if (FORCES || LAST) {
                     const int u = lane + 32 * i;
