@@ -279,7 +279,7 @@ class Harness:
         self.world = int(os.environ.get("WORLD_SIZE", "1"))
         torch.cuda.set_device(self.local_rank)
         self.dev = torch.device("cuda", self.local_rank)
-        if self.world > 1:
+        if self.world > 1 and not os.environ.get("MB_BENCH_NO_BIND"):
             bind_to_gpu_numa_node(self.local_rank)            # pinned host buffers land next to this GPU
             dist.init_process_group("nccl", device_id=self.dev)
 
@@ -297,6 +297,8 @@ class Harness:
         torch.cuda.synchronize()
         sync()
         sampler = ClockSampler(self.local_rank)
+        if os.environ.get("MB_BENCH_NO_SAMPLER"):
+            sampler.h = None
         sampler.start()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         c0 = counter()
@@ -420,26 +422,32 @@ def gather_cost(h):
     res = {"workload": f"PotvinFuglevandMuscle(120) x {per_rank} per rank x {K} steps, FP64 mode, totals of every rank on every rank",
            "unit": "ms per window (max over ranks)"}
     try:
-        sb = ShardedMuscleBatch(MuscleSpec.potvin(N_UNITS), per_rank * h.world, h.dev, "f64", fresh_outputs=False)
+        def fresh():                                          # every leg starts from rested muscles: the kernel's time
+            return ShardedMuscleBatch(MuscleSpec.potvin(N_UNITS), per_rank * h.world, h.dev, "f64",   # drifts with the state
+                                      fresh_outputs=False)
         gen = torch.Generator(device=h.dev).manual_seed(4 + h.rank)
         e = (67.0 * (0.5 + 0.5 * torch.rand(per_rank, device=h.dev, generator=gen, dtype=torch.float64))).repeat(K, 1).contiguous()
         sink = torch.zeros((), dtype=torch.float64, device=h.dev)
+        peer_of = (h.rank + 1) % h.world                      # consume the totals that came from the next rank
 
-        def run(mode):
+        def run(sb, mode):
             if mode == "peer":
-                views = sb.step_many_peer_gather(e, 0.02, dense=False)
-                sink.add_(sum(v[-1].sum() for v in views))
+                sink.add_(sb.step_many_peer_gather(e, 0.02, dense=False)[peer_of][-1].sum())
             elif mode == "nccl":
                 sink.add_(sb.step_many(e, 0.02, gather=True)[-1].sum())
             else:
                 sink.add_(sb.step_many(e, 0.02)[-1].sum())
 
         for mode in ("none", "nccl"):
-            sec, _ = h.timed(lambda: run(mode), 5, 2)
+            sb = fresh()
+            sec, _ = h.timed(lambda: run(sb, mode), 5, 2)
             res[mode + "_ms"] = round(1e3 * sec / 5, 3)
+            del sb
         try:
+            sb = fresh()
             sb.enable_peer_gather(K)
-            sec, _ = h.timed(lambda: run("peer"), 5, 2)
+            res["peer_stores"] = "nvlink multicast (multimem.st)" if sb._pg.get("multicast") else "one store per peer"
+            sec, _ = h.timed(lambda: run(sb, "peer"), 5, 2)
             res["peer_ms"] = round(1e3 * sec / 5, 3)
             res["peer_over_none"] = round(res["peer_ms"] / res["none_ms"], 4)
         except Exception as exc:                               # symmetric memory unavailable on this box
@@ -744,9 +752,13 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.gpus > 1 and world == 1:
         # convenience: re-launch under torchrun, one rank per GPU
+        import socket
         import subprocess
+        with socket.socket() as sock:                         # a free port: back-to-back launches must not collide
+            sock.bind(("127.0.0.1", 0))
+            port = sock.getsockname()[1]
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
-               "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
+               "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
         return subprocess.call(cmd)
     return run_gpu_arm(args)
 
