@@ -279,8 +279,9 @@ class Harness:
         self.world = int(os.environ.get("WORLD_SIZE", "1"))
         torch.cuda.set_device(self.local_rank)
         self.dev = torch.device("cuda", self.local_rank)
-        if self.world > 1 and not os.environ.get("MB_BENCH_NO_BIND"):
-            bind_to_gpu_numa_node(self.local_rank)            # pinned host buffers land next to this GPU
+        if self.world > 1:
+            if not os.environ.get("MB_BENCH_NO_BIND"):
+                bind_to_gpu_numa_node(self.local_rank)        # pinned host buffers land next to this GPU
             dist.init_process_group("nccl", device_id=self.dev)
 
     def barrier(self):
@@ -294,13 +295,15 @@ class Harness:
         for _ in range(warmup):
             fn()
         join()
-        torch.cuda.synchronize()
-        sync()
+        # the sampler's NVML start-up takes milliseconds and differs between ranks: do it BEFORE the barrier, or a
+        # region with a cross-rank dependency (a gather) is charged the skew between the ranks' start times
         sampler = ClockSampler(self.local_rank)
         if os.environ.get("MB_BENCH_NO_SAMPLER"):
             sampler.h = None
         sampler.start()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        sync()
         c0 = counter()
         a.record()
         for _ in range(steps):
@@ -440,15 +443,17 @@ def gather_cost(h):
 
         for mode in ("none", "nccl"):
             sb = fresh()
-            sec, _ = h.timed(lambda: run(sb, mode), 5, 2)
+            sec, clk = h.timed(lambda: run(sb, mode), 5, 2)
             res[mode + "_ms"] = round(1e3 * sec / 5, 3)
+            res[mode + "_sm_mhz"] = clk.get("sm_mhz")
             del sb
         try:
             sb = fresh()
             sb.enable_peer_gather(K)
             res["peer_stores"] = "nvlink multicast (multimem.st)" if sb._pg.get("multicast") else "one store per peer"
-            sec, _ = h.timed(lambda: run(sb, "peer"), 5, 2)
+            sec, clk = h.timed(lambda: run(sb, "peer"), 5, 2)
             res["peer_ms"] = round(1e3 * sec / 5, 3)
+            res["peer_sm_mhz"] = clk.get("sm_mhz")
             res["peer_over_none"] = round(res["peer_ms"] / res["none_ms"], 4)
         except Exception as exc:                               # symmetric memory unavailable on this box
             res["peer_error"] = f"{type(exc).__name__}: {exc}"[:300]
