@@ -1,6 +1,8 @@
 #!/bin/bash
-# final 8-GPU headline line (gather trio timed from rested batches)
+# final 8-GPU lines: headline (with the gather trio) and config 4 with the fused gather
 set -u
 mkdir -p gpurun_out
-timeout 900 python bench.py --gpus 8 > gpurun_out/bench_n8.json 2> gpurun_out/bench_n8.err
+timeout 200 python bench.py --gpus 8 > gpurun_out/bench_n8.json 2> gpurun_out/bench_n8.err
 grep "^{" gpurun_out/bench_n8.json | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('value %.4g e2e %.4g'%(d['value'], d['e2e']['value']), d['roofline']['gather_config4'])"
+timeout 120 python bench.py --gpus 8 --config 4 > gpurun_out/bench_c4_n8.json 2> gpurun_out/bench_c4_n8.err
+grep "^{" gpurun_out/bench_c4_n8.json | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('c4 value %.4g ms %.3f'%(d['value'], d['ms_per_step']))"
