@@ -1,5 +1,5 @@
 #!/bin/bash
-# final 8-GPU lines: headline (with the gather trio) and config 4 with the fused gather
+# 8-GPU lines of the final code: headline (with the gather trio) and config 4 with the fused gather (gpurun --gpus 8)
 set -u
 mkdir -p gpurun_out
 timeout 200 python bench.py --gpus 8 > gpurun_out/bench_n8.json 2> gpurun_out/bench_n8.err
